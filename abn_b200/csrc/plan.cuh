@@ -1,0 +1,231 @@
+// plan.cuh - per-candidate design resolution and everything that needs only the global Gram.
+//
+// The global Gram G = Z^T Z is computed once per data set over
+//     Z = [ 1 | every stored column | log(y + 0.1) for every Poisson node ]
+// so that (a) Gaussian children (either method) are scored with no data pass at all
+// (src/irls_gaussian_fast.cpp:34-49, src/node_gaussian.c), (b) the least-squares start values of
+// the Bayes solvers (generate_inits_n*, src/node_binomial.c:832-883, src/node_poisson.c:705-763,
+// src/node_gaussian.c:743-808) and (c) the rank test of rank_cpp (src/rank.cpp:15, called at
+// R/build_score_cache_mle.R:282) come from k x k sub-blocks instead of n x k passes.
+#pragma once
+
+#include "solver.cuh"
+
+namespace abn {
+
+// device-resident description of the data set
+struct DataMeta {
+    long long n;     // observations
+    long long ld;    // leading dimension (elements) of the column-major matrix
+    int n_nodes, n_cols;
+    int D;           // Gram dimension = 1 + n_cols + n_nodes
+    const double *X; // column-major, ld x n_cols
+    const double *G; // D x D row-major symmetric
+    const int *node_family; // [n_nodes]
+    const int *node_col0;   // [n_nodes + 1]
+    const double *node_lfact; // [n_nodes] sum lgamma(y + 1) (Poisson nodes, else 0)
+};
+
+ABN_HD int gram_icpt() { return 0; }
+ABN_HD int gram_col(int c) { return 1 + c; }
+ABN_HD int gram_logy(const DataMeta &m, int node) { return 1 + m.n_cols + node; }
+
+// one candidate's resolved design
+struct FitDesc {
+    int cols[MAXK];       // stored column of design column j (-1 = intercept)
+    int ycol;             // first stored column of the child
+    short k;              // design columns after rank handling
+    short kdata;          // selected stored columns before rank handling (for MDL)
+    short num_na;         // leading columns dropped (binomial, rank deficient)
+    short family;         // child family
+    short rank;           // rank of the full design as rank_cpp sees it
+    short err;            // 1 = design wider than MAXK
+};
+
+// kernel bucket of a resolved fit: family-specific streaming kernels are instantiated per
+// (k, intercept); Gaussian fits go to the Gram-only kernel.
+ABN_HD int bucket_of(const FitDesc &d)
+{
+    if (d.err) return 0;
+    if (d.family == GAUSSIAN) return 1;
+    int icpt = (d.k > 0 && d.cols[0] < 0) ? 1 : 0;
+    int fam = d.family == BINOMIAL ? 0 : (d.family == POISSON ? 1 : 2);
+    return 2 + (fam * (MAXK + 1) + d.k) * 2 + icpt;
+}
+constexpr int NBUCKETS = 2 + 3 * (MAXK + 1) * 2;
+
+ABN_HD int gidx(const FitDesc &d, int j) { return d.cols[j] < 0 ? 0 : 1 + d.cols[j]; }
+
+// k x k Gram block of the design, MAXM-strided
+ABN_HD void gram_block(const DataMeta &m, const FitDesc &d, int j0, int k, double *A)
+{
+    for (int i = 0; i < k; i++)
+        for (int j = 0; j < k; j++)
+            A_(A, i, j) = m.G[(long long)gidx(d, j0 + i) * m.D + gidx(d, j0 + j)];
+}
+
+// arma::rank of the n x k design from the eigenvalues of its Gram block: singular values
+// sqrt(lambda_i) against max(n,k) * sigma_max * eps, with the floor FP64 accumulation of the
+// Gram imposes on what can be told from zero.
+ABN_HDN int gram_rank(const DataMeta &m, const FitDesc &d, int j0, int k)
+{
+    if (k <= 0) return 0;
+    double A[MAXM * MAXM], V[MAXM * MAXM], w[MAXM];
+    gram_block(m, d, j0, k, A);
+    jacobi_eig(A, k, w, V);
+    double lmax = 0.0;
+    for (int i = 0; i < k; i++) if (w[i] > lmax) lmax = w[i];
+    const double eps = 2.220446049250313e-16;
+    double nn = (double)(m.n > k ? m.n : k);
+    double tol_sv = nn * sqrt(lmax) * eps;
+    double noise = fmax(64.0, 8.0 * sqrt((double)m.n)) * k * eps * lmax;
+    double thr = fmax(tol_sv * tol_sv, noise);
+    int r = 0;
+    for (int i = 0; i < k; i++) if (w[i] > thr) r++;
+    return r;
+}
+
+// forLoopContent's design assembly, R/build_score_cache_mle.R:254-306 (mle) and
+// build_designmatrix, src/node_binomial.c:497-572 (bayes)
+ABN_HDN void resolve_design(const DataMeta &m, int method, int child, const int *parents, int width, FitDesc &d)
+{
+    d.family = (short)m.node_family[child];
+    d.ycol = m.node_col0[child];
+    d.num_na = 0;
+    d.err = 0;
+    bool any_multi = false;
+    int kdata = 0;
+    for (int j = 0; j < width; j++) {
+        int p = parents[j];
+        if (p < 0) continue;
+        if (m.node_family[p] == MULTINOMIAL) any_multi = true;
+        kdata += m.node_col0[p + 1] - m.node_col0[p];
+    }
+    bool icpt = (method == BAYES) || !any_multi; // _mle.R:266-270
+    int k = kdata + (icpt ? 1 : 0);
+    d.kdata = (short)kdata;
+    for (int j = 0; j < MAXK; j++) d.cols[j] = -1;
+    if (k > MAXK) { d.err = 1; d.k = 0; d.rank = 0; return; }
+    int c = 0;
+    if (icpt) d.cols[c++] = -1;
+    for (int j = 0; j < width; j++) {
+        int p = parents[j];
+        if (p < 0) continue;
+        for (int col = m.node_col0[p]; col < m.node_col0[p + 1]; col++) d.cols[c++] = col;
+    }
+    d.k = (short)k;
+    d.rank = (short)k;
+    if (method == MLE) {
+        int R = gram_rank(m, d, 0, k);                         // _mle.R:282
+        d.rank = (short)R;
+        if (R != k && d.family == BINOMIAL) {                  // _mle.R:286-294: drop leading columns
+            int j0 = 0;
+            while (k - j0 > 0 && gram_rank(m, d, j0, k - j0) != k - j0) j0++;
+            for (int j = 0; j + j0 < k; j++) d.cols[j] = d.cols[j + j0];
+            // a dropped intercept leaves only data columns; mark slot 0 accordingly
+            d.k = (short)(k - j0);
+            d.num_na = (short)j0;
+            for (int j = d.k; j < MAXK; j++) d.cols[j] = -1;
+        }
+    }
+}
+
+// ---- Gaussian child, method = "mle": src/irls_gaussian_fast.cpp:34-49 from Gram blocks ---------
+ABN_HDN void gauss_mle_fit(const DataMeta &m, const FitDesc &d, double *loglik, double *aic, double *bic, int *status)
+{
+    const int k = d.k;
+    double A[MAXM * MAXM], S[MAXM * MAXM], b[MAXM], x[MAXM];
+    gram_block(m, d, 0, k, A);
+    const long long gy = gram_col(d.ycol);
+    for (int i = 0; i < k; i++) b[i] = m.G[(long long)gidx(d, i) * m.D + gy];
+    int st = sym_solve(A, b, k, true, x, S);
+    double yy = m.G[gy * m.D + gy];
+    double xb = 0.0, xax = 0.0;
+    for (int i = 0; i < k; i++) {
+        double t = 0.0;
+        for (int j = 0; j < k; j++) t += A_(A, i, j) * x[j];
+        xax += t * x[i];
+        xb += b[i] * x[i];
+    }
+    double ssr = yy - 2.0 * xb + xax; // ||y - X x||^2
+    double n = (double)m.n, df = k + 1;
+    double ll = 0.5 * (-n * (log(2 * M_PI) + 1 - log(n) + log(ssr)));
+    *loglik = ll;
+    *aic = -2 * ll + 2 * df;
+    *bic = -2 * ll + log(n) * df;
+    *status = (st < 0 || !isfinite(ll)) ? FIT_NON_FINITE : FIT_OK;
+}
+
+// ---- Bayes start values: beta0 = inv(X'X) X'y~ by LU, as generate_inits_n* do -------------------
+// y~ = y (binomial, Gaussian) or log(y + 0.1) (Poisson). Gaussian also gets tau0 = (n - m)/RSS.
+ABN_HDN void bayes_inits(const DataMeta &m, const FitDesc &d, int child, FitState &s)
+{
+    const int k = d.k;
+    double A[MAXM * MAXM], inv[MAXM * MAXM], b[MAXM], e[MAXM], col[MAXM];
+    int perm[MAXM];
+    gram_block(m, d, 0, k, A);
+    const long long gy = (d.family == POISSON) ? gram_logy(m, child) : gram_col(d.ycol);
+    for (int i = 0; i < k; i++) b[i] = m.G[(long long)gidx(d, i) * m.D + gy];
+    lu_decomp(A, k, perm);
+    bool singular = lu_singular(A, k);
+    double beta[MAXM];
+    if (!singular) {
+        for (int j = 0; j < k; j++) {
+            for (int i = 0; i < k; i++) e[i] = (i == j) ? 1.0 : 0.0;
+            lu_solve(A, perm, k, e, col);
+            for (int i = 0; i < k; i++) A_(inv, i, j) = col[i];
+        }
+        for (int i = 0; i < k; i++) {
+            double t = 0.0;
+            for (int j = 0; j < k; j++) t += A_(inv, i, j) * b[j];
+            beta[i] = t;
+        }
+    } else {
+        for (int i = 0; i < k; i++) beta[i] = (d.family == GAUSSIAN) ? 0.01 : 0.0;
+    }
+    for (int i = 0; i < k; i++) s.x0[i] = beta[i];
+    if (d.family == GAUSSIAN) {
+        gram_block(m, d, 0, k, A);
+        double yy = m.G[gy * m.D + gy];
+        double xb = 0.0, xax = 0.0;
+        for (int i = 0; i < k; i++) {
+            double t = 0.0;
+            for (int j = 0; j < k; j++) t += A_(A, i, j) * beta[j];
+            xax += t * beta[i];
+            xb += b[i] * beta[i];
+        }
+        double rss = yy - 2.0 * xb + xax;
+        s.x0[k] = 1.0 / (rss / ((double)m.n - (double)k));
+    }
+}
+
+// the "pass" of a Gaussian Bayes fit is a Gram lookup: H = X'X, g = X'y, ll = y'y
+ABN_HD void gauss_gram_acc(const DataMeta &m, const FitDesc &d, PassAcc &a)
+{
+    const int k = d.k;
+    const long long gy = gram_col(d.ycol);
+    for (int i = 0; i < k; i++) {
+        for (int j = i; j < k; j++) a.H[tri(i, j, k)] = m.G[(long long)gidx(d, i) * m.D + gidx(d, j)];
+        a.g[i] = m.G[(long long)gidx(d, i) * m.D + gy];
+    }
+    a.ll = m.G[gy * m.D + gy];
+    a.bad = 0;
+}
+
+// common state setup
+ABN_HD void state_setup(const DataMeta &m, const FitDesc &d, int child, const Control &c, FitState &s)
+{
+    s.family = d.family;
+    s.k = d.k;
+    s.M = d.k + ((c.method == BAYES && d.family == GAUSSIAN) ? 1 : 0);
+    s.n = (double)m.n;
+    s.lfact = m.node_lfact[child];
+}
+
+// MDL of a scored mle row: bic + (1 + #selected stored columns - num.na) * log(nvars), _mle.R:343
+ABN_HD double mdl_of(double bic, const FitDesc &d, int nvars)
+{
+    return bic + (double)(1 + d.kdata - d.num_na) * log((double)nvars);
+}
+
+} // namespace abn

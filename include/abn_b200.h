@@ -1,0 +1,202 @@
+/*
+ * abn_b200.h - C ABI of the B200-native score-cache path of abn (furrer-lab/abn v3.1.13).
+ *
+ * This is the drop-in boundary: a plain-C shared library (libabn_b200.so, built from
+ * abn_b200/csrc/ with nvcc for sm_100a).  No R, Rcpp, torch or C++ types cross it; every
+ * pointer is caller-owned and never retained after the call returns (device state lives
+ * behind the opaque abn_data handle).  INTEGRATION.md shows the R .Call shim a maintainer
+ * adds to src/ and the R_CallMethodDef rows for src/RcppExports.cpp:122-138.
+ *
+ * Reference interfaces replaced (all paths relative to the reference tree):
+ *
+ *   abn_b200_enumerate      <- buildcachematrix()         src/buildcachematrix.c:15-141
+ *                              + isretained()             src/buildcachematrix.c:150-162
+ *                              + combn enumeration        R/build_score_cache_mle.R:432-518
+ *   abn_b200_node_defn      <- node.defn matrix assembly  R/build_score_cache_bayes.R:82-85
+ *   abn_b200_score_cache    <- the per-candidate loops    R/build_score_cache_mle.R:615-703
+ *                                                         R/build_score_cache_bayes.R:121-214
+ *                              and everything they call:
+ *                                rank_cpp                 src/rank.cpp:15
+ *                                irls_gaussian_cpp_fast   src/irls_gaussian_fast.cpp:12
+ *                                irls_binomial_cpp_fast_br src/irls_binomial_fast_br.cpp:15
+ *                                irls_poisson_cpp_fast    src/irls_poisson_fast.cpp:16
+ *                                nnet.default softmax fit R/build_score_cache_mle.R:319-331
+ *                                fit_single_node          src/fit_single_node.c:25
+ *                                calc_node_Score_binary   src/node_binomial.c:18
+ *                                calc_node_Score_gaus     src/node_gaussian.c:18
+ *                                calc_node_Score_pois     src/node_poisson.c:20
+ *   abn_b200_data_create /  <- make_data() (copies the whole data frame per candidate,
+ *   abn_b200_data_destroy      src/utility.c:106-141); here it is done once per cache
+ *   abn_b200_score          <- same as abn_b200_score_cache, on an already resident data set
+ *
+ * Conventions: all node / column indices that cross this ABI are 0-based unless a comment
+ * says otherwise; matrices are column-major (R layout) unless a comment says otherwise;
+ * all floating point is IEEE double.
+ */
+#ifndef ABN_B200_H
+#define ABN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABN_B200_VERSION 100 /* 0.1.0 */
+
+/* node families: the codes of get.var.types() (R/abn-internal.R:833) plus multinomial */
+enum {
+    ABN_BINOMIAL = 1,
+    ABN_GAUSSIAN = 2,
+    ABN_POISSON = 3,
+    ABN_MULTINOMIAL = 4
+};
+
+enum {
+    ABN_METHOD_MLE = 0,  /* buildScoreCache(method = "mle")   */
+    ABN_METHOD_BAYES = 1 /* buildScoreCache(method = "bayes") */
+};
+
+/* Bayes root finder: what locates the mode of the Laplace integrand */
+enum {
+    ABN_SOLVER_NEWTON = 0, /* full Newton steps with the analytic Hessian, run to the epsabs test */
+    ABN_SOLVER_HYBRID = 1  /* Powell hybrid (MINPACK HYBRJ as in GSL hybridsj / hybridj), the
+                              reference's iterate sequence and its error.code = 1 outcomes */
+};
+
+/* per-fit status: the reference's error.code (src/node_binomial.c:117,152,192-193) */
+enum {
+    ABN_FIT_OK = 0,
+    ABN_FIT_NOT_CONVERGED = 1, /* solver left without meeting its stop rule               */
+    ABN_FIT_NON_FINITE = 2     /* score is NaN / a non-finite weight or Gram was met       */
+};
+
+/* return codes of the entry points */
+enum {
+    ABN_OK = 0,
+    ABN_ERR_ARG = -1,     /* bad argument (message says which)                            */
+    ABN_ERR_CUDA = -2,    /* CUDA runtime error (message carries cudaGetErrorString)      */
+    ABN_ERR_NO_GPU = -3,  /* no CUDA device / kernel image not loadable - there is no CPU path */
+    ABN_ERR_LIMIT = -4,   /* design wider than ABN_MAX_K columns                           */
+    ABN_ERR_ALLOC = -5
+};
+
+#define ABN_MAX_K 16 /* widest design matrix (intercept + expanded parent columns) */
+
+/*
+ * The data set, already prepared as the R drivers prepare it before their loops
+ * (R/build_score_cache_mle.R:398-415,563-599; R/build_score_cache_bayes.R:40-60):
+ * Gaussian columns centred and scaled, binomial columns 0/1, Poisson columns counts,
+ * multinomial nodes one-hot expanded with ALL levels kept.
+ */
+typedef struct abn_dataset {
+    int64_t n;                  /* observations                                              */
+    int32_t n_nodes;            /* d: variables / nodes                                      */
+    int32_t n_cols;             /* stored columns = sum over nodes of their column counts    */
+    const double *X;            /* column-major n x n_cols                                   */
+    const int32_t *node_family; /* [n_nodes] ABN_BINOMIAL ...                                */
+    const int32_t *node_col0;   /* [n_nodes + 1] node i owns columns node_col0[i] .. node_col0[i+1]-1
+                                   (one column, or nlevels columns for a multinomial node)   */
+} abn_dataset;
+
+/*
+ * The candidate list: one (child, parent set) per row, in the order of the cache.
+ * parents is row-major rows x max_parents, each row ascending, padded with -1.
+ */
+typedef struct abn_candidates {
+    int64_t rows;
+    int32_t max_parents;    /* row width of parents[]                                       */
+    const int32_t *child;   /* [rows] 0-based node id                                       */
+    const int32_t *parents; /* [rows * max_parents] 0-based node ids, -1 = unused slot      */
+} abn_candidates;
+
+/* build.control() scalars that reach the natives (R/build_score_cache.R:90-127,
+ * R/build_score_cache_bayes.R:314-328) */
+typedef struct abn_control {
+    int32_t method;     /* ABN_METHOD_MLE / ABN_METHOD_BAYES                                */
+    int32_t max_iters;  /* control$max.iters (100)                                           */
+    double tol;         /* mle: control$tol (1e-8), ||x - x_old||_2 stop                     */
+    double epsabs;      /* bayes: control$epsabs (1e-7), sum |grad g| stop                   */
+    double prior_mean;  /* bayes: control$mean (0)                                           */
+    double prior_sd;    /* bayes: 1/sqrt(control$prec) (prec = 0.001)                        */
+    double gam_shape;   /* bayes: control$loggam.shape (1)                                   */
+    double gam_scale;   /* bayes: 1/control$loggam.inv.scale (inv.scale = 5e-05)             */
+    int32_t solver;     /* bayes: ABN_SOLVER_*                                               */
+    int32_t device;     /* CUDA device ordinal this call runs on (one process per GPU)       */
+    int32_t nvars;      /* MDL: number of variables in log(nvars), R/build_score_cache_mle.R:343 */
+    int32_t reserved;
+} abn_control;
+
+/* Output arrays, all caller-allocated with `rows` entries; any pointer may be NULL.
+ * mle fills mlik (= log-likelihood), aic, bic, mdl; bayes fills mlik only. */
+typedef struct abn_result {
+    double *mlik;
+    double *aic;
+    double *bic;
+    double *mdl;
+    int32_t *status; /* ABN_FIT_*                                                            */
+    int32_t *iters;  /* data passes / solver iterations executed, for the roofline account   */
+} abn_result;
+
+typedef struct abn_data abn_data; /* opaque: device-resident data set + its global Gram     */
+
+/* fills *c with build.control() defaults for `method` */
+void abn_b200_default_control(int32_t method, abn_control *c);
+
+int32_t abn_b200_version(void);
+
+/* number of CUDA devices visible; 0 with no driver. Never fails. */
+int32_t abn_b200_device_count(void);
+
+/*
+ * Candidate enumeration, bit-exact with buildcachematrix (and hence with the mle combn path,
+ * tests/testthat/test-build_score_cache.R:174-184): for every node in which_nodes, for
+ * j = 0 .. max_parents[node], all j-subsets of {0..d-1} in lexicographic order, dropping
+ * subsets that contain the node, contain a banned arc or miss a retained arc.
+ *
+ * banned / retained: d x d column-major 0/1, entry [child + parent * d] (utility.c:35).
+ * Call once with children == parents == NULL to get *rows, then again with storage:
+ * children [rows] 0-based; parents [rows * width] row-major, -1 padded, where
+ * width = max over which_nodes of max_parents[node].
+ */
+int abn_b200_enumerate(int32_t d, const int32_t *banned, const int32_t *retained,
+                       const int32_t *max_parents, const int32_t *which_nodes, int32_t n_which,
+                       int64_t *rows, int32_t *width, int32_t *children, int32_t *parents,
+                       char *err, size_t errlen);
+
+/* expands the compact parent lists to the rows x d 0/1 integer matrix `node.defn`,
+ * column-major as R stores it */
+int abn_b200_node_defn(const abn_candidates *cand, int32_t d, int32_t *node_defn,
+                       char *err, size_t errlen);
+
+/* uploads the data set to ctrl-independent device storage on `device` and computes the
+ * global Gram matrix once */
+int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_data **out,
+                         char *err, size_t errlen);
+void abn_b200_data_destroy(abn_data *d);
+
+/* scores `cand` on a resident data set; synchronous (results are in host memory on return) */
+int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn_control *ctrl,
+                   abn_result *out, char *err, size_t errlen);
+
+/* one-shot: data_create + score + data_destroy */
+int abn_b200_score_cache(const abn_dataset *ds, const abn_candidates *cand,
+                         const abn_control *ctrl, abn_result *out, char *err, size_t errlen);
+
+/* instrumentation of the last abn_b200_score on this handle: device milliseconds by phase and
+ * kernel launches issued (bench.py's gpu_launches). Any pointer may be NULL. */
+typedef struct abn_timing {
+    double h2d_ms;      /* candidate upload                                                  */
+    double plan_ms;     /* design resolution / rank / work-list build                        */
+    double fit_ms;      /* all fit kernels                                                   */
+    double d2h_ms;      /* result download                                                   */
+    int64_t launches;   /* kernels launched                                                  */
+    int64_t algo_bytes; /* sum over fits of passes * n * (k_data + 1) * 8         */
+} abn_timing;
+int abn_b200_last_timing(const abn_data *d, abn_timing *t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABN_B200_H */

@@ -1,0 +1,126 @@
+// host_sim.cpp - TEST INFRASTRUCTURE. Drives the product's __host__ __device__ solver state
+// machines (abn_b200/csrc/solver.cuh, rowops.cuh, plan.cuh) on the CPU with plain sequential
+// row loops standing in for the CUDA data passes. It lets the -m "not gpu" suite check the
+// exact control flow the kernels execute (step control, stop rules, flags, Gram-based start
+// values and rank handling) against the oracle and the reference's golden caches in a
+// container without a GPU. It is not part of libabn_b200.so and nothing in abn_b200/ loads it.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../abn_b200/csrc/plan.cuh"
+#include "../abn_b200/csrc/rowops.cuh"
+#include "../abn_b200/csrc/solver.cuh"
+#include "../include/abn_b200.h"
+
+using namespace abn;
+
+namespace {
+
+template <int KIND>
+void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode, PassAcc &a)
+{
+    const int k = d.k;
+    std::memset(&a, 0, sizeof(a));
+    RowConst rc = make_row_const(k, (double)m.n);
+    const double *y = m.X + (size_t)d.ycol * m.ld;
+    double x[MAXK];
+    for (long long i = 0; i < m.n; i++) {
+        double eta = 0.0;
+        for (int j = 0; j < k; j++) {
+            x[j] = d.cols[j] < 0 ? 1.0 : m.X[(size_t)d.cols[j] * m.ld + i];
+            eta += x[j] * beta[j];
+        }
+        double w, r, l = 0.0;
+        RowOp<KIND>::template apply<true>(eta, y[i], rc, w, r, l, a.bad);
+        if (mode != PASS_GRAD)
+            for (int p = 0; p < k; p++)
+                for (int q = p; q < k; q++) a.H[tri(p, q, k)] += w * x[p] * x[q];
+        if (mode != PASS_HESS)
+            for (int p = 0; p < k; p++) a.g[p] += r * x[p];
+        a.ll += l;
+    }
+}
+
+void run_pass(const DataMeta &m, const FitDesc &d, const Control &c, const FitState &s, int mode, PassAcc &a)
+{
+    if (mode == PASS_PINIT) { host_pass<RK_PINIT>(m, d, s.x, PASS_FULL, a); return; }
+    if (d.family == POISSON) { host_pass<RK_POIS>(m, d, s.x, mode, a); return; }
+    if (c.method == MLE) host_pass<RK_BIN_MLE>(m, d, s.x, mode, a);
+    else host_pass<RK_BIN_BAYES>(m, d, s.x, mode, a);
+}
+
+} // namespace
+
+extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand, const abn_control *ctrl,
+                               abn_result *out, int *buckets /* optional [rows] */)
+{
+    const long long n = ds->n;
+    const int D = 1 + ds->n_cols + ds->n_nodes;
+    // Z = [1 | X | log(y + 0.1) of Poisson nodes], G = Z'Z
+    std::vector<double> G((size_t)D * D, 0.0), lfact(ds->n_nodes, 0.0);
+    std::vector<const double *> zc(D, nullptr);
+    std::vector<std::vector<double>> extra;
+    std::vector<double> ones(n, 1.0);
+    zc[0] = ones.data();
+    for (int c = 0; c < ds->n_cols; c++) zc[1 + c] = ds->X + (size_t)c * n;
+    extra.resize(ds->n_nodes);
+    for (int v = 0; v < ds->n_nodes; v++) {
+        if (ds->node_family[v] != ABN_POISSON) continue;
+        const double *y = ds->X + (size_t)ds->node_col0[v] * n;
+        extra[v].resize(n);
+        for (long long i = 0; i < n; i++) { extra[v][i] = std::log(y[i] + 0.1); lfact[v] += std::lgamma(y[i] + 1.0); }
+        zc[1 + ds->n_cols + v] = extra[v].data();
+    }
+    for (int a = 0; a < D; a++) {
+        if (!zc[a]) continue;
+        for (int b = a; b < D; b++) {
+            if (!zc[b]) continue;
+            double s = 0.0;
+            for (long long i = 0; i < n; i++) s += zc[a][i] * zc[b][i];
+            G[(size_t)a * D + b] = G[(size_t)b * D + a] = s;
+        }
+    }
+    DataMeta m{n, n, ds->n_nodes, ds->n_cols, D, ds->X, G.data(), ds->node_family, ds->node_col0, lfact.data()};
+    Control c{ctrl->method, ctrl->max_iters, ctrl->solver, ctrl->nvars, ctrl->tol, ctrl->epsabs,
+              ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale};
+
+#pragma omp parallel for schedule(dynamic, 8)
+    for (long long r = 0; r < cand->rows; r++) {
+        FitDesc d;
+        const int child = cand->child[r];
+        resolve_design(m, c.method, child, cand->parents + r * cand->max_parents, cand->max_parents, d);
+        if (buckets) buckets[r] = bucket_of(d);
+        double ll = NAN, aic = NAN, bic = NAN, mdl = NAN;
+        int status = FIT_NON_FINITE, passes = 0;
+        if (d.err || d.family == MULTINOMIAL || d.k == 0) {
+            // not supported by this build
+        } else if (c.method == MLE && d.family == GAUSSIAN) {
+            gauss_mle_fit(m, d, &ll, &aic, &bic, &status);
+            passes = 1;
+        } else {
+            FitState s;
+            std::memset(&s, 0, sizeof(s));
+            state_setup(m, d, child, c, s);
+            if (c.method == BAYES) bayes_inits(m, d, child, s);
+            PassAcc a;
+            int mode = fit_begin(s, c);
+            while (mode != PASS_DONE) {
+                if (d.family == GAUSSIAN) gauss_gram_acc(m, d, a);
+                else run_pass(m, d, c, s, mode, a);
+                mode = fit_consume(s, c, a);
+            }
+            ll = s.loglik; aic = s.aic; bic = s.bic; status = s.status;
+            passes = d.family == GAUSSIAN ? 1 : s.passes;
+        }
+        if (c.method == MLE) mdl = mdl_of(bic, d, c.nvars);
+        if (out->mlik) out->mlik[r] = ll;
+        if (out->aic) out->aic[r] = aic;
+        if (out->bic) out->bic[r] = bic;
+        if (out->mdl) out->mdl[r] = mdl;
+        if (out->status) out->status[r] = status;
+        if (out->iters) out->iters[r] = passes;
+    }
+    return 0;
+}
