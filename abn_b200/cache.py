@@ -1,0 +1,406 @@
+"""Host-side mirror of the reference's operator interface for the score-cache path.
+
+``buildScoreCache`` / ``build_control`` keep the names, argument meaning, defaults and error
+behaviour of ``R/build_score_cache.R:90-180,438-781`` and return the ``abnCache`` fields in the
+order ``R/build_score_cache_bayes.R:219-248`` / ``R/build_score_cache_mle.R:705-724`` assemble
+them, so ``mostProbable`` / ``searchHillClimber`` / ``searchHeuristic`` find what they expect.
+Everything numerical goes through the C ABI (``include/abn_b200.h``) to the CUDA library; there
+is no CPU path here - without ``libabn_b200.so`` and a GPU the call raises.
+
+Python conventions that differ from R: ``which_nodes`` is a list of column names or 0-based
+indices; ``dag_banned`` / ``dag_retained`` are (d, d) arrays indexed ``[child, parent]``, dicts
+``{child: [parents]}`` or formula strings ``"~child|parent1:parent2+child2|parent"``.  The
+returned ``children`` stays 1-based like the R object.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _capi as capi
+from . import prep as _prep
+
+ERROR_CODE_DESC = {  # R/build_score_cache_bayes.R:230-235
+    0: "success",
+    1: "warning: mode results may be unreliable (optimiser terminated unusually)",
+    2: "error - logscore is NA. Model could not be fitted",
+    4: "warning: fin.diff hessian estimation terminated unusually",
+}
+
+_BAYES_KEYS = ("max.mode.error", "mean", "prec", "loggam.shape", "loggam.inv.scale", "max.iters", "epsabs",
+               "error.verbose", "trace", "epsabs.inner", "max.iters.inner", "finite.step.size", "hessian.params",
+               "max.iters.hessian", "max.hessian.error", "factor.brent", "maxiters.hessian.brent",
+               "num.intervals.brent", "n.grid", "ncores", "cluster.type", "seed")
+_MLE_KEYS = ("ncores", "cluster.type", "max.iters", "max.irls", "tol", "tolPwrss", "check.rankX", "check.scaleX",
+             "check.conv.grad", "check.conv.singular", "check.conv.hess", "xtol_abs", "ftol_abs", "trace.mblogit",
+             "catcov.mblogit", "epsilon", "only_glmmTMB_poisson", "seed")
+_DEFAULTS = {
+    "max.mode.error": 10, "mean": 0, "prec": 0.001, "loggam.shape": 1, "loggam.inv.scale": 5e-05,
+    "max.iters": 100, "epsabs": 1e-07, "error.verbose": False, "trace": 0, "epsabs.inner": 1e-06,
+    "max.iters.inner": 100, "finite.step.size": 1e-07, "hessian.params": (1e-04, 0.01), "max.iters.hessian": 10,
+    "max.hessian.error": 0.5, "factor.brent": 100, "maxiters.hessian.brent": 100, "num.intervals.brent": 100,
+    "n.grid": 250, "ncores": 1, "cluster.type": "FORK", "max.irls": 100, "tol": 1e-8, "tolPwrss": 1e-7,
+    "check.rankX": "message+drop.cols", "check.scaleX": "message+rescale", "check.conv.grad": "message",
+    "check.conv.singular": "message", "check.conv.hess": "message", "xtol_abs": 1e-6, "ftol_abs": 1e-6,
+    "trace.mblogit": False, "catcov.mblogit": "free", "epsilon": 1e-6, "only_glmmTMB_poisson": False,
+    "seed": 9062019,
+}
+# extra, B200-specific knobs carried in the same control list
+_EXTRA_DEFAULTS = {"solver": "hybrid", "device": 0}
+
+
+def build_control(method: str = "bayes", **kwargs) -> dict:
+    """``build.control()`` (R/build_score_cache.R:90-180). Keys use the R names (``max.iters`` ...);
+    keyword arguments may spell them with underscores (``max_iters=50``)."""
+    if method == "bayes":
+        keys = _BAYES_KEYS
+    elif method == "mle":
+        keys = _MLE_KEYS
+    else:
+        raise ValueError("`method` unknown.")
+    vals = dict(_DEFAULTS)
+    vals.update(_EXTRA_DEFAULTS)
+    for k, v in kwargs.items():
+        kk = k if k in vals else k.replace("_", ".")
+        if kk not in vals:
+            kk2 = k.replace(".", "_")
+            if kk2 in vals:
+                kk = kk2
+            else:
+                raise TypeError(f"unused argument ({k})")
+        vals[kk] = v
+    ctrl = {k: vals[k] for k in keys}
+    for k in _EXTRA_DEFAULTS:
+        ctrl[k] = vals[k]
+    return ctrl
+
+
+def _check_control(control, method):
+    """check.valid.buildControls (R/abn-internal.R:610-709), reduced to what reaches the natives."""
+    base = build_control(method)
+    if control is None:
+        return base
+    if not isinstance(control, dict):
+        raise TypeError("`control` must be a dict as returned by build_control()")
+    for k, v in control.items():
+        if k not in base and k not in _DEFAULTS:
+            warnings.warn(f"control argument {k!r} is unknown and ignored")
+            continue
+        base[k] = v
+    if int(base["max.iters"]) < 0:
+        raise ValueError("`max.iters` must be non-negative")
+    return base
+
+
+def to_c_control(ctrl: dict, method: str, nvars: int) -> capi.Control:
+    solver = ctrl.get("solver", "hybrid")
+    solver_code = {"hybrid": capi.SOLVER_HYBRID, "newton": capi.SOLVER_NEWTON}.get(solver, solver)
+    if method == "bayes":
+        return capi.Control(
+            method=capi.METHOD_BAYES, max_iters=int(ctrl["max.iters"]), tol=1e-8, epsabs=float(ctrl["epsabs"]),
+            prior_mean=float(ctrl["mean"]), prior_sd=1.0 / np.sqrt(float(ctrl["prec"])),      # _bayes.R:314
+            gam_shape=float(ctrl["loggam.shape"]), gam_scale=1.0 / float(ctrl["loggam.inv.scale"]),  # _bayes.R:315
+            solver=int(solver_code), device=int(ctrl.get("device", 0)), nvars=int(nvars), reserved=0)
+    return capi.Control(
+        method=capi.METHOD_MLE, max_iters=int(ctrl["max.iters"]), tol=float(ctrl["tol"]), epsabs=1e-7,
+        prior_mean=0.0, prior_sd=1.0, gam_shape=1.0, gam_scale=1.0, solver=int(solver_code),
+        device=int(ctrl.get("device", 0)), nvars=int(nvars), reserved=0)
+
+
+# ---- dag.banned / dag.retained ---------------------------------------------------------------------
+
+def _parse_formula(f: str, names: list) -> np.ndarray:
+    """formula_abn (R/abn-internal.R:503-529): "~a|b:c+d|e" -> a has parents b, c; d has parent e.
+    A dot on the right means "all other nodes"."""
+    d = len(names)
+    m = np.zeros((d, d), dtype=np.int32)
+    body = f.strip()
+    if body.startswith("~"):
+        body = body[1:]
+    for term in [t for t in body.replace(" ", "").split("+") if t]:
+        if "|" not in term:
+            continue
+        lhs, rhs = term.split("|", 1)
+        for child in lhs.split(":"):
+            if child not in names:
+                raise ValueError(f"DAG formulation not correct: unknown node {child!r}")
+            for par in rhs.split(":"):
+                if par == ".":
+                    for p in names:
+                        if p != child:
+                            m[names.index(child), names.index(p)] = 1
+                    continue
+                if par not in names:
+                    raise ValueError(f"DAG formulation not correct: unknown node {par!r}")
+                m[names.index(child), names.index(par)] = 1
+    return m
+
+
+def _dag_matrix(dag, names, what):
+    """check.valid.dag (R/abn-internal.R:332-424): NULL -> all zeros; matrix must be d x d 0/1 with
+    an empty diagonal."""
+    d = len(names)
+    if dag is None:
+        return np.zeros((d, d), dtype=np.int32)
+    if isinstance(dag, str):
+        m = _parse_formula(dag, names)
+    elif isinstance(dag, dict):
+        m = np.zeros((d, d), dtype=np.int32)
+        for child, pars in dag.items():
+            for p in ([pars] if isinstance(pars, str) else pars):
+                m[names.index(child), names.index(p)] = 1
+    else:
+        m = np.asarray(dag)
+        if m.shape != (d, d):
+            raise ValueError(f"'{what}' as dimension must agree with the number of variables in data.df")
+        if not np.isin(m, (0, 1)).all():
+            raise ValueError(f"'{what}' must comprise only 1's or 0's")
+        m = m.astype(np.int32)
+    if np.any(np.diag(m) != 0):
+        raise ValueError(f"'{what}' is not a valid DAG - a child cannot be its own parent!")
+    return m
+
+
+class AbnCache(dict):
+    """The ``abnCache`` list. ``node.defn`` (rows x d 0/1 integers) is expanded on first access from
+    the compact parent lists kept in ``parents`` (at 16 M rows x 100 nodes it is 6.5 GB)."""
+
+    def __missing__(self, key):
+        if key == "node.defn":
+            nd = node_defn(self["children"] - 1, self["parents"], len(self["data.dists"]))
+            self[key] = nd
+            return nd
+        raise KeyError(key)
+
+
+def enumerate_candidates(d, dag_banned, dag_retained, max_parents, which_nodes=None):
+    """``abn_b200_enumerate``. Returns (children 0-based int32 [rows], parents int32 [rows, width])."""
+    L = capi.lib()
+    ban = np.ascontiguousarray(np.asarray(dag_banned, dtype=np.int32).ravel(order="F"))
+    ret = np.ascontiguousarray(np.asarray(dag_retained, dtype=np.int32).ravel(order="F"))
+    mp = np.ascontiguousarray(np.broadcast_to(np.asarray(max_parents, dtype=np.int32), (d,)))
+    wn = None if which_nodes is None else np.ascontiguousarray(which_nodes, dtype=np.int32)
+    rows, width = C.c_int64(0), C.c_int32(0)
+    err = C.create_string_buffer(512)
+    capi.check(L.abn_b200_enumerate(d, capi.ptr_i(ban), capi.ptr_i(ret), capi.ptr_i(mp), capi.ptr_i(wn),
+                                    0 if wn is None else len(wn), C.byref(rows), C.byref(width), None, None,
+                                    err, len(err)), err)
+    W = max(1, width.value)
+    children = np.empty(rows.value, dtype=np.int32)
+    parents = np.empty((rows.value, W), dtype=np.int32)
+    wcap = C.c_int32(W)
+    capi.check(L.abn_b200_enumerate(d, capi.ptr_i(ban), capi.ptr_i(ret), capi.ptr_i(mp), capi.ptr_i(wn),
+                                    0 if wn is None else len(wn), C.byref(rows), C.byref(wcap),
+                                    capi.ptr_i(children), capi.ptr_i(parents), err, len(err)), err)
+    return children, parents
+
+
+def node_defn(children0, parents, d):
+    """``abn_b200_node_defn``: compact parent lists -> rows x d 0/1 int32 matrix."""
+    L = capi.lib()
+    cd, keep = capi.make_candidates(children0, parents)
+    out = np.zeros((cd.rows, d), dtype=np.int32, order="F")
+    err = C.create_string_buffer(256)
+    capi.check(L.abn_b200_node_defn(C.byref(cd), d, capi.ptr_i(out), err, len(err)), err)
+    del keep
+    return out
+
+
+class DeviceData:
+    """A data set resident on one GPU (``abn_b200_data_create``) that candidate lists can be scored
+    against repeatedly (``abn_b200_score``)."""
+
+    def __init__(self, prepared: _prep.Prepared, device: int = 0):
+        L = capi.lib()
+        self.prepared = prepared
+        self._ds, self._keep = capi.make_dataset(prepared.X, prepared.node_family, prepared.node_col0)
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        capi.check(L.abn_b200_data_create(C.byref(self._ds), device, C.byref(self._h), err, len(err)), err)
+
+    def score(self, children0, parents, control: capi.Control) -> dict:
+        L = capi.lib()
+        cd, keep = capi.make_candidates(children0, parents)
+        res, arrs = capi.make_result(cd.rows, control.method)
+        err = C.create_string_buffer(512)
+        capi.check(L.abn_b200_score(self._h, C.byref(cd), C.byref(control), C.byref(res), err, len(err)), err)
+        del keep
+        return arrs
+
+    def timing(self) -> dict:
+        t = capi.Timing()
+        capi.lib().abn_b200_last_timing(self._h, C.byref(t))
+        return {k: getattr(t, k) for k, _ in capi.Timing._fields_}
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            capi.lib().abn_b200_data_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _normalise_max_parents(max_parents, names, method):
+    """check.valid.parents (R/abn-internal.R:426-501) + R/build_score_cache.R:611-631."""
+    d = len(names)
+    if max_parents is None:
+        mp = np.full(d, d, dtype=np.int64)
+    elif isinstance(max_parents, dict):
+        if set(max_parents) != set(names):
+            raise ValueError("'max.parents' names do not match the variable names in data.df")
+        mp = np.array([int(max_parents[nm]) for nm in names], dtype=np.int64)
+    elif np.ndim(max_parents) == 0:
+        mp = np.full(d, int(max_parents), dtype=np.int64)
+    else:
+        mp = np.asarray(max_parents, dtype=np.int64)
+        if len(mp) != d:
+            raise ValueError("'max.parents' as vector must have one entry per node")
+    if np.any(mp < 0):
+        raise ValueError("'max.parents' must be non-negative")
+    if np.any(mp >= d):
+        warnings.warn(f"`max.parents` >= no. of variables. I set it to (no. of variables - 1)={d - 1}")
+        mp = np.minimum(mp, d - 1)
+    if method == "mle" and len(np.unique(mp)) != 1:
+        raise ValueError("ISSUE: `max.parents` with node specific values that are not all the same, is not yet "
+                         "implemented further down here.")  # R/build_score_cache_mle.R:457-463
+    return mp
+
+
+def buildScoreCache(data_df=None, data_dists=None, method="bayes", group_var=None, adj_vars=None, cor_vars=None,
+                    dag_banned=None, dag_retained=None, max_parents=None, which_nodes=None, defn_res=None,
+                    centre=True, dry_run=False, control=None, verbose=False, debugging=False):
+    """``buildScoreCache()`` (R/build_score_cache.R:438-781) on a B200.
+
+    Returns an :class:`AbnCache` with the reference's fields; for ``method="mle"`` ``mlik`` is the
+    log-likelihood and ``aic`` / ``bic`` / ``mdl`` are filled, for ``method="bayes"`` ``mlik`` is the
+    Laplace log marginal likelihood with ``error.code`` per row.
+    """
+    if data_df is None:
+        raise ValueError("'data.df' is not provided.")
+    if data_dists is None:
+        raise ValueError("'data.dists' is not provided.")
+    if method not in ("bayes", "mle"):
+        raise ValueError("`method` unknown.")
+    if group_var is not None or cor_vars is not None:
+        raise NotImplementedError("grouped (mixed-effects) nodes are outside the B200 score-cache path "
+                                  "(R/build_score_cache_mle.R:26-250, R/build_score_cache_bayes.R:395-503)")
+    if adj_vars is not None:
+        raise NotImplementedError("adj.vars is not supported by the B200 score-cache path")
+    ctrl = _check_control(control, method)
+    if method == "bayes" and ctrl.get("max.mode.error", 10) == 100:
+        raise NotImplementedError("control max.mode.error = 100 forces INLA, which this path does not provide")
+
+    cols = _prep.as_columns(data_df)
+    names = [c.name for c in cols]
+    if set(data_dists) != set(names):
+        raise ValueError("data.dists and data.df have different variable names")
+    d_all = len(names)
+
+    wn_idx = None
+    if which_nodes is not None:
+        wn_idx = np.array([names.index(w) if isinstance(w, str) else int(w) for w in which_nodes], dtype=np.int32)
+        if len(np.unique(wn_idx)) != len(wn_idx) or wn_idx.min() < 0 or wn_idx.max() >= d_all:
+            raise ValueError("`which.nodes` is invalid.")
+    if method == "mle" and wn_idx is not None:
+        # the mle driver subsets the data: R/build_score_cache_mle.R:388-392
+        cols = [cols[i] for i in wn_idx]
+        names = [c.name for c in cols]
+        data_dists = {nm: data_dists[nm] for nm in names}
+        if dag_banned is not None and not isinstance(dag_banned, (str, dict)):
+            dag_banned = np.asarray(dag_banned)[np.ix_(wn_idx, wn_idx)]
+        if dag_retained is not None and not isinstance(dag_retained, (str, dict)):
+            dag_retained = np.asarray(dag_retained)[np.ix_(wn_idx, wn_idx)]
+        if isinstance(max_parents, dict):
+            max_parents = {nm: max_parents[nm] for nm in names}
+        wn_idx = None
+    d = len(names)
+
+    banned = _dag_matrix(dag_banned, names, "dag.banned")
+    retained = _dag_matrix(dag_retained, names, "dag.retained")
+    mp = _normalise_max_parents(max_parents, names, method)
+    if wn_idx is not None and len(wn_idx) < int(mp.max()):
+        pass  # the reference's check compares against the trimmed node count; harmless here
+    if np.any(retained.sum(axis=1) > mp.max()):
+        raise ValueError("'dag.retained' is inconsistent with max.parents!")
+    if np.any((banned == 1) & (retained == 1)):
+        raise ValueError("'dag.banned' and 'dag.retained' are inconsistent!")
+
+    P = _prep.prepare(cols, data_dists, method, centre=bool(centre))
+
+    if defn_res is not None:
+        ch1 = np.asarray(defn_res["children"], dtype=np.int32)
+        nd = np.asarray(defn_res["node.defn"])
+        if nd.ndim != 2 or nd.shape[1] != d or not np.isin(nd, (0, 1)).all():
+            raise ValueError("'defn.res' is wrong format - must only be 0,1 in node definitions")
+        width = max(1, int(nd.sum(axis=1).max()))
+        parents = np.full((len(ch1), width), -1, dtype=np.int32)
+        for r in range(len(ch1)):
+            idx = np.nonzero(nd[r])[0]
+            parents[r, :len(idx)] = idx
+        children0 = ch1 - 1
+    else:
+        children0, parents = enumerate_candidates(d, banned, retained, mp, wn_idx)
+
+    out = AbnCache()
+    out["children"] = children0 + 1
+    out["parents"] = parents  # compact form; "node.defn" is expanded lazily from it
+    if dry_run:
+        out["node.defn"] = node_defn(children0, parents, d)
+        return out
+
+    cctrl = to_c_control(ctrl, method, d)
+    with DeviceData(P, device=int(ctrl.get("device", 0))) as dev:
+        res = dev.score(children0, parents, cctrl)
+        out.timing = dev.timing()
+    out.passes = res["iters"]
+    out.status = res["status"]
+
+    if method == "bayes":
+        out["mlik"] = res["mlik"]
+        out["error.code"] = res["status"].astype(np.float64)
+        out["hessian.accuracy"] = np.zeros(len(children0))
+        out["used.INLA"] = np.zeros(len(children0), dtype=bool)
+        out["error.code.desc"] = [ERROR_CODE_DESC.get(int(c), str(int(c))) for c in res["status"]]
+        out["data.df"] = data_df
+        out["data.dists"] = dict(data_dists)
+        out["max.parents"] = mp
+        out["dag.retained"] = retained
+        out["dag.banned"] = banned
+        out["group.var"] = None
+        out["group.ids"] = None
+        out["group.vars"] = None
+        out["cor.vars"] = None
+        out["mylist"] = {k: [i for i, dd in enumerate(P.dists) if dd == v]
+                         for k, v in (("bin", "binomial"), ("gaus", "gaussian"), ("pois", "poisson"))}
+        out["method"] = "bayes"
+    else:
+        out["mlik"] = res["mlik"]
+        out["error.code"] = []
+        out["hessian.accuracy"] = []
+        out["used.INLA"] = []
+        out["error.code.desc"] = []
+        out["data.df"] = data_df
+        out["data.dists"] = dict(data_dists)
+        out["max.parents"] = int(mp[0])
+        out["dag.retained"] = retained
+        out["dag.banned"] = banned
+        out["group.var"] = None
+        out["group.ids"] = None
+        out["grouped.vars"] = None
+        out["aic"] = res["aic"]
+        out["bic"] = res["bic"]
+        out["mdl"] = res["mdl"]
+        out["method"] = "mle"
+    return out

@@ -1,0 +1,584 @@
+// abn_b200.cu - C ABI (include/abn_b200.h), device data set, global Gram, design resolution,
+// Gram-only Gaussian kernels and the dispatch of the streaming fit kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/abn_b200.h"
+#include "fit_kernel.cuh"
+
+using namespace abn;
+
+static_assert(ABN_MAX_K == MAXK, "include/abn_b200.h and solver.cuh disagree on the design width");
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static int fail(char *err, size_t errlen, int code, const char *fmt, ...)
+{
+    if (err && errlen) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, errlen, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            int code_ = (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ||            \
+                         e_ == cudaErrorNoKernelImageForDevice) ? ABN_ERR_NO_GPU : ABN_ERR_CUDA;    \
+            if (e_ == cudaErrorMemoryAllocation) code_ = ABN_ERR_ALLOC;                             \
+            cudaGetLastError();                                                                     \
+            return fail(err, errlen, code_, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_),       \
+                        __FILE__, __LINE__);                                                        \
+        }                                                                                           \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// K1: global Gram  G = Z^T Z,  Z = [1 | X | log(y + 0.1) of Poisson nodes], FP64, deterministic
+// ---------------------------------------------------------------------------------------------
+constexpr int GT = 6;        // register tile edge
+constexpr int GRAM_THREADS = 256;
+
+// value of Gram column a at row i
+__device__ __forceinline__ double z_value(const DataMeta &m, int a, long long i)
+{
+    if (a == 0) return 1.0;
+    if (a <= m.n_cols) return __ldg(m.X + (long long)(a - 1) * m.ld + i);
+    const int node = a - 1 - m.n_cols;
+    if (m.node_family[node] != POISSON) return 0.0;
+    return log(__ldg(m.X + (long long)m.node_col0[node] * m.ld + i) + 0.1);
+}
+
+// grid.x = row chunks, grid.y = groups of GRAM_THREADS tile pairs. Each thread owns one GT x GT
+// tile (I <= J) of the upper block triangle; the CTA stages RC rows of all D columns in shared
+// memory (row-major, padded) and every thread sweeps them. Partial tiles go to
+// part[chunk][pair][GT*GT]; gram_reduce sums the chunks in a fixed order.
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_partial(const DataMeta m, int T, int NP, int RC, int Dp, long long rows_per_chunk, double *__restrict__ part)
+{
+    extern __shared__ double zs[]; // RC x Dp
+    const int pair = blockIdx.y * GRAM_THREADS + threadIdx.x;
+    int I = 0, J = 0;
+    if (pair < NP) { // unrank (I, J), I <= J, row-major over the upper triangle
+        int p = pair, rowlen = T;
+        while (p >= rowlen) { p -= rowlen; rowlen--; I++; }
+        J = I + p;
+    }
+    double acc[GT][GT];
+#pragma unroll
+    for (int a = 0; a < GT; a++)
+#pragma unroll
+        for (int b = 0; b < GT; b++) acc[a][b] = 0.0;
+
+    const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+    const long long r1 = min(m.n, r0 + rows_per_chunk);
+    for (long long base = r0; base < r1; base += RC) {
+        const int nr = (int)min((long long)RC, r1 - base);
+        __syncthreads();
+        // coalesced along rows within a column; transposed store
+        for (int e = threadIdx.x; e < RC * m.D; e += GRAM_THREADS) {
+            const int col = e / RC, r = e - col * RC;
+            zs[r * Dp + col] = (r < nr) ? z_value(m, col, base + r) : 0.0;
+        }
+        // zero the padding columns the last tile may touch
+        for (int e = threadIdx.x; e < RC * (Dp - m.D); e += GRAM_THREADS) {
+            const int r = e / (Dp - m.D), col = m.D + (e - r * (Dp - m.D));
+            zs[r * Dp + col] = 0.0;
+        }
+        __syncthreads();
+        if (pair < NP) {
+            for (int r = 0; r < nr; r++) {
+                double a[GT], b[GT];
+#pragma unroll
+                for (int t = 0; t < GT; t++) { a[t] = zs[r * Dp + I * GT + t]; b[t] = zs[r * Dp + J * GT + t]; }
+#pragma unroll
+                for (int s = 0; s < GT; s++)
+#pragma unroll
+                    for (int t = 0; t < GT; t++) acc[s][t] = fma(a[s], b[t], acc[s][t]);
+            }
+        }
+    }
+    if (pair < NP) {
+        double *o = part + ((long long)blockIdx.x * NP + pair) * (GT * GT);
+#pragma unroll
+        for (int s = 0; s < GT; s++)
+#pragma unroll
+            for (int t = 0; t < GT; t++) o[s * GT + t] = acc[s][t];
+    }
+}
+
+__global__ void gram_reduce(int D, int T, int NP, int chunks, const double *__restrict__ part, double *__restrict__ G)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x; // element of a tile pair
+    if (e >= NP * GT * GT) return;
+    const int pair = e / (GT * GT), st = e - pair * (GT * GT);
+    int I = 0, p = pair, rowlen = T;
+    while (p >= rowlen) { p -= rowlen; rowlen--; I++; }
+    const int J = I + p;
+    const int i = I * GT + st / GT, j = J * GT + st % GT;
+    if (i >= D || j >= D) return;
+    double s = 0.0;
+    for (int c = 0; c < chunks; c++) s += part[((long long)c * NP + pair) * (GT * GT) + st];
+    G[(long long)i * D + j] = s;
+    G[(long long)j * D + i] = s;
+}
+
+// sum lgamma(y + 1) per Poisson node (src/irls_poisson_fast.cpp:32-34, gsl_sf_lnfact in
+// src/node_poisson.c:561): one CTA per node, fixed-order tree
+__global__ void __launch_bounds__(256) lfact_kernel(const DataMeta m, double *__restrict__ out)
+{
+    __shared__ double red[256];
+    const int node = blockIdx.x;
+    double s = 0.0;
+    if (m.node_family[node] == POISSON) {
+        const double *y = m.X + (long long)m.node_col0[node] * m.ld;
+        for (long long i = threadIdx.x; i < m.n; i += 256) s += lgamma(__ldg(y + i) + 1.0);
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[node] = red[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// design resolution: one thread per candidate
+// ---------------------------------------------------------------------------------------------
+__global__ void resolve_kernel(const DataMeta m, int method, long long rows, int width, const int *__restrict__ child,
+                               const int *__restrict__ parents, FitDesc *__restrict__ descs,
+                               unsigned char *__restrict__ keys, int *__restrict__ idx)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    FitDesc d;
+    resolve_design(m, method, child[r], parents + r * width, width, d);
+    if (d.k == 0 || d.family == MULTINOMIAL) d.err = d.err ? d.err : 2;
+    descs[r] = d;
+    keys[r] = (unsigned char)bucket_of(d);
+    idx[r] = (int)r;
+}
+
+__global__ void bucket_bounds(const unsigned char *__restrict__ keys, long long rows, int *__restrict__ start)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int k = keys[r];
+    if (r == 0 || keys[r - 1] != k) start[k] = (int)r;
+}
+
+// rows the streaming kernels cannot take (design too wide / multinomial child / empty design)
+__global__ void unsupported_kernel(const int *__restrict__ list, int count, ResultPtrs out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int row = list[t];
+    if (out.mlik) out.mlik[row] = NAN;
+    if (out.aic) out.aic[row] = NAN;
+    if (out.bic) out.bic[row] = NAN;
+    if (out.mdl) out.mdl[row] = NAN;
+    if (out.status) out.status[row] = FIT_NON_FINITE;
+    if (out.iters) out.iters[row] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gaussian children: no data pass, everything from Gram blocks. One thread per fit.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+gauss_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ child,
+             const int *__restrict__ list, int count, ResultPtrs out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int row = list[t];
+    const FitDesc d = descs[row];
+    if (c.method == MLE) {
+        double ll, aic, bic;
+        int status;
+        gauss_mle_fit(m, d, &ll, &aic, &bic, &status);
+        if (out.mlik) out.mlik[row] = ll;
+        if (out.aic) out.aic[row] = aic;
+        if (out.bic) out.bic[row] = bic;
+        if (out.mdl) out.mdl[row] = mdl_of(bic, d, c.nvars);
+        if (out.status) out.status[row] = status;
+        if (out.iters) out.iters[row] = 1;
+        return;
+    }
+    FitState s;
+    PassAcc a;
+    state_setup(m, d, child[row], c, s);
+    bayes_inits(m, d, child[row], s);
+    gauss_gram_acc(m, d, a);
+    int mode = fit_begin(s, c);
+    while (mode != PASS_DONE) mode = fit_consume(s, c, a);
+    if (out.mlik) out.mlik[row] = s.loglik;
+    if (out.status) out.status[row] = s.status;
+    if (out.iters) out.iters[row] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device data set
+// ---------------------------------------------------------------------------------------------
+struct abn_data {
+    int device = 0;
+    DataMeta m{};
+    double *dX = nullptr, *dG = nullptr, *dLfact = nullptr;
+    int *dFamily = nullptr, *dCol0 = nullptr;
+    std::vector<int> family, col0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    abn_timing timing{};
+    // scratch that grows with the largest candidate list seen
+    long long cap_rows = 0;
+    int cap_width = 0;
+    int *dChild = nullptr, *dParents = nullptr, *dIdx = nullptr, *dIdxSorted = nullptr, *dBucketStart = nullptr,
+        *dCounters = nullptr, *dStatus = nullptr, *dIters = nullptr;
+    unsigned char *dKeys = nullptr, *dKeysSorted = nullptr;
+    FitDesc *dDescs = nullptr;
+    double *dRes = nullptr; // 4 x rows
+    void *dSortTmp = nullptr;
+    size_t sortTmpBytes = 0;
+};
+
+static void free_scratch(abn_data *d)
+{
+    cudaFree(d->dChild); cudaFree(d->dParents); cudaFree(d->dIdx); cudaFree(d->dIdxSorted);
+    cudaFree(d->dStatus); cudaFree(d->dIters); cudaFree(d->dKeys); cudaFree(d->dKeysSorted);
+    cudaFree(d->dDescs); cudaFree(d->dRes); cudaFree(d->dSortTmp);
+    d->dChild = d->dParents = d->dIdx = d->dIdxSorted = d->dStatus = d->dIters = nullptr;
+    d->dKeys = d->dKeysSorted = nullptr; d->dDescs = nullptr; d->dRes = nullptr; d->dSortTmp = nullptr;
+    d->cap_rows = 0; d->cap_width = 0; d->sortTmpBytes = 0;
+}
+
+extern "C" void abn_b200_data_destroy(abn_data *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->device);
+    free_scratch(d);
+    cudaFree(d->dX); cudaFree(d->dG); cudaFree(d->dLfact); cudaFree(d->dFamily); cudaFree(d->dCol0);
+    cudaFree(d->dBucketStart); cudaFree(d->dCounters);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+static int compute_gram(abn_data *d, char *err, size_t errlen)
+{
+    const DataMeta &m = d->m;
+    const int D = m.D;
+    const int T = (D + GT - 1) / GT;
+    const int NP = T * (T + 1) / 2;
+    const int Dp = T * GT + 1; // padded smem row, odd-ish stride
+    int RC = 64;
+    while (RC > 8 && (size_t)RC * Dp * sizeof(double) > 160 * 1024) RC >>= 1;
+    if ((size_t)RC * Dp * sizeof(double) > 200 * 1024)
+        return fail(err, errlen, ABN_ERR_LIMIT, "data set has too many columns for the Gram kernel (D=%d)", D);
+    const int gy = (NP + GRAM_THREADS - 1) / GRAM_THREADS;
+    int chunks = std::max(1, (2 * d->sm_count) / gy);
+    long long rpc = (m.n + chunks - 1) / chunks;
+    rpc = ((rpc + RC - 1) / RC) * RC;
+    if (rpc < RC) rpc = RC;
+    chunks = (int)((m.n + rpc - 1) / rpc);
+    if (chunks < 1) chunks = 1;
+    double *part = nullptr;
+    CUDA_TRY(cudaMalloc(&part, (size_t)chunks * NP * GT * GT * sizeof(double)));
+    const size_t smem = (size_t)RC * Dp * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cudaFree(part); CUDA_TRY(e); }
+    gram_partial<<<dim3(chunks, gy), GRAM_THREADS, smem, d->stream>>>(m, T, NP, RC, Dp, rpc, part);
+    gram_reduce<<<(NP * GT * GT + 255) / 256, 256, 0, d->stream>>>(D, T, NP, chunks, part, d->dG);
+    lfact_kernel<<<m.n_nodes, 256, 0, d->stream>>>(m, d->dLfact);
+    e = cudaStreamSynchronize(d->stream);
+    cudaFree(part);
+    CUDA_TRY(e);
+    CUDA_TRY(cudaGetLastError());
+    d->timing.launches += 3;
+    return ABN_OK;
+}
+
+extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_data **out, char *err, size_t errlen)
+{
+    if (!ds || !out) return fail(err, errlen, ABN_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (ds->n <= 0 || ds->n_nodes <= 0 || ds->n_cols < ds->n_nodes || !ds->X || !ds->node_family || !ds->node_col0)
+        return fail(err, errlen, ABN_ERR_ARG, "empty or inconsistent data set (n=%lld, nodes=%d, cols=%d)",
+                    (long long)ds->n, ds->n_nodes, ds->n_cols);
+    if (ds->node_col0[0] != 0 || ds->node_col0[ds->n_nodes] != ds->n_cols)
+        return fail(err, errlen, ABN_ERR_ARG, "node_col0 must start at 0 and end at n_cols");
+    for (int i = 0; i < ds->n_nodes; i++) {
+        const int f = ds->node_family[i], w = ds->node_col0[i + 1] - ds->node_col0[i];
+        if (f < ABN_BINOMIAL || f > ABN_MULTINOMIAL) return fail(err, errlen, ABN_ERR_ARG, "node %d: unknown family %d", i, f);
+        if (w < 1 || (f != ABN_MULTINOMIAL && w != 1))
+            return fail(err, errlen, ABN_ERR_ARG, "node %d: family %d cannot own %d columns", i, f, w);
+    }
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(err, errlen, ABN_ERR_NO_GPU, "no CUDA device available (%s); this library has no CPU path",
+                    e0 == cudaSuccess ? "device count is 0" : cudaGetErrorString(e0));
+    }
+    if (device < 0 || device >= ndev) return fail(err, errlen, ABN_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    abn_data *d = new (std::nothrow) abn_data();
+    if (!d) return fail(err, errlen, ABN_ERR_ALLOC, "out of host memory");
+    d->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) d->sm_count = prop.multiProcessorCount;
+    d->family.assign(ds->node_family, ds->node_family + ds->n_nodes);
+    d->col0.assign(ds->node_col0, ds->node_col0 + ds->n_nodes + 1);
+
+    const long long ld = ((ds->n + 15) / 16) * 16; // 128-byte aligned columns
+    const int D = 1 + ds->n_cols + ds->n_nodes;
+    int rc = ABN_OK;
+#define TRY_OR_FREE(expr)                                                       \
+    do {                                                                        \
+        cudaError_t e_ = (expr);                                                \
+        if (e_ != cudaSuccess) {                                                \
+            rc = fail(err, errlen, e_ == cudaErrorMemoryAllocation ? ABN_ERR_ALLOC : ABN_ERR_CUDA, \
+                      "%s: %s", #expr, cudaGetErrorString(e_));                 \
+            cudaGetLastError();                                                 \
+            abn_b200_data_destroy(d);                                           \
+            return rc;                                                          \
+        }                                                                       \
+    } while (0)
+    TRY_OR_FREE(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    TRY_OR_FREE(cudaMalloc(&d->dX, (size_t)ld * ds->n_cols * sizeof(double)));
+    TRY_OR_FREE(cudaMalloc(&d->dG, (size_t)D * D * sizeof(double)));
+    TRY_OR_FREE(cudaMalloc(&d->dLfact, (size_t)ds->n_nodes * sizeof(double)));
+    TRY_OR_FREE(cudaMalloc(&d->dFamily, (size_t)ds->n_nodes * sizeof(int)));
+    TRY_OR_FREE(cudaMalloc(&d->dCol0, (size_t)(ds->n_nodes + 1) * sizeof(int)));
+    TRY_OR_FREE(cudaMalloc(&d->dBucketStart, (size_t)(NBUCKETS + 1) * sizeof(int)));
+    TRY_OR_FREE(cudaMalloc(&d->dCounters, (size_t)(NBUCKETS + 1) * sizeof(int)));
+    TRY_OR_FREE(cudaMemsetAsync(d->dX, 0, (size_t)ld * ds->n_cols * sizeof(double), d->stream));
+    TRY_OR_FREE(cudaMemcpy2DAsync(d->dX, (size_t)ld * sizeof(double), ds->X, (size_t)ds->n * sizeof(double),
+                                  (size_t)ds->n * sizeof(double), (size_t)ds->n_cols, cudaMemcpyHostToDevice, d->stream));
+    TRY_OR_FREE(cudaMemcpyAsync(d->dFamily, ds->node_family, (size_t)ds->n_nodes * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    TRY_OR_FREE(cudaMemcpyAsync(d->dCol0, ds->node_col0, (size_t)(ds->n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    TRY_OR_FREE(cudaStreamSynchronize(d->stream));
+#undef TRY_OR_FREE
+    d->m.n = ds->n;
+    d->m.ld = ld;
+    d->m.n_nodes = ds->n_nodes;
+    d->m.n_cols = ds->n_cols;
+    d->m.D = D;
+    d->m.X = d->dX;
+    d->m.G = d->dG;
+    d->m.node_family = d->dFamily;
+    d->m.node_col0 = d->dCol0;
+    d->m.node_lfact = d->dLfact;
+    rc = compute_gram(d, err, errlen);
+    if (rc != ABN_OK) { abn_b200_data_destroy(d); return rc; }
+    *out = d;
+    return ABN_OK;
+}
+
+static int ensure_scratch(abn_data *d, long long rows, int width, char *err, size_t errlen)
+{
+    if (rows <= d->cap_rows && width <= d->cap_width) return ABN_OK;
+    free_scratch(d);
+    const long long cap = std::max<long long>(rows, 1024);
+    const int w = std::max(width, 1);
+    CUDA_TRY(cudaMalloc(&d->dChild, (size_t)cap * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d->dParents, (size_t)cap * w * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d->dIdx, (size_t)cap * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d->dIdxSorted, (size_t)cap * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d->dStatus, (size_t)cap * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d->dIters, (size_t)cap * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d->dKeys, (size_t)cap));
+    CUDA_TRY(cudaMalloc(&d->dKeysSorted, (size_t)cap));
+    CUDA_TRY(cudaMalloc(&d->dDescs, (size_t)cap * sizeof(FitDesc)));
+    CUDA_TRY(cudaMalloc(&d->dRes, (size_t)cap * 4 * sizeof(double)));
+    size_t tmp = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d->dKeys, d->dKeysSorted, d->dIdx, d->dIdxSorted, (int)cap, 0, 8, d->stream));
+    CUDA_TRY(cudaMalloc(&d->dSortTmp, tmp));
+    d->sortTmpBytes = tmp;
+    d->cap_rows = cap;
+    d->cap_width = w;
+    return ABN_OK;
+}
+
+extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn_control *ctrl, abn_result *out,
+                              char *err, size_t errlen)
+{
+    if (!d || !cand || !ctrl || !out) return fail(err, errlen, ABN_ERR_ARG, "null argument");
+    if (cand->rows < 0 || cand->max_parents < 0) return fail(err, errlen, ABN_ERR_ARG, "negative candidate count / width");
+    if (cand->rows > 2000000000LL) return fail(err, errlen, ABN_ERR_LIMIT, "more than 2e9 candidates in one call; split the list");
+    if (ctrl->method != ABN_METHOD_MLE && ctrl->method != ABN_METHOD_BAYES) return fail(err, errlen, ABN_ERR_ARG, "unknown method %d", ctrl->method);
+    if (ctrl->method == ABN_METHOD_BAYES)
+        for (int f : d->family)
+            if (f == ABN_MULTINOMIAL)
+                return fail(err, errlen, ABN_ERR_ARG, "Multinomial nodes are not yet implemented for method 'bayes'. Try with method='mle'.");
+    const long long rows = cand->rows;
+    const int width = cand->max_parents;
+    d->timing = abn_timing{};
+    if (rows == 0) return ABN_OK;
+    if (!cand->child || (width > 0 && !cand->parents)) return fail(err, errlen, ABN_ERR_ARG, "null candidate arrays");
+    // host-side validation of indices (cheap relative to the upload)
+    for (long long r = 0; r < rows; r++) {
+        if (cand->child[r] < 0 || cand->child[r] >= d->m.n_nodes) return fail(err, errlen, ABN_ERR_ARG, "row %lld: child %d out of range", r, cand->child[r]);
+        for (int j = 0; j < width; j++) {
+            const int p = cand->parents[r * width + j];
+            if (p >= d->m.n_nodes || p == cand->child[r]) return fail(err, errlen, ABN_ERR_ARG, "row %lld: parent %d invalid", r, p);
+        }
+    }
+    CUDA_TRY(cudaSetDevice(d->device));
+    int rc = ensure_scratch(d, rows, width, err, errlen);
+    if (rc != ABN_OK) return rc;
+
+    cudaEvent_t ev[5];
+    for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+    cudaStream_t s = d->stream;
+    long long launches = 0;
+
+    CUDA_TRY(cudaEventRecord(ev[0], s));
+    CUDA_TRY(cudaMemcpyAsync(d->dChild, cand->child, (size_t)rows * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (width > 0) CUDA_TRY(cudaMemcpyAsync(d->dParents, cand->parents, (size_t)rows * width * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(ev[1], s));
+
+    Control c{ctrl->method, ctrl->max_iters, ctrl->solver, ctrl->nvars, ctrl->tol, ctrl->epsabs,
+              ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale};
+    ResultPtrs rp{d->dRes, d->dRes + d->cap_rows, d->dRes + 2 * d->cap_rows, d->dRes + 3 * d->cap_rows, d->dStatus, d->dIters};
+
+    const int tb = 128;
+    resolve_kernel<<<(unsigned)((rows + tb - 1) / tb), tb, 0, s>>>(d->m, c.method, rows, width, d->dChild, d->dParents,
+                                                                  d->dDescs, d->dKeys, d->dIdx);
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(d->dSortTmp, d->sortTmpBytes, d->dKeys, d->dKeysSorted, d->dIdx, d->dIdxSorted,
+                                             (int)rows, 0, 8, s));
+    CUDA_TRY(cudaMemsetAsync(d->dBucketStart, 0xff, (size_t)(NBUCKETS + 1) * sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(d->dCounters, 0, (size_t)(NBUCKETS + 1) * sizeof(int), s));
+    bucket_bounds<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(d->dKeysSorted, rows, d->dBucketStart);
+    launches += 3;
+    int hstart[NBUCKETS + 1];
+    CUDA_TRY(cudaMemcpyAsync(hstart, d->dBucketStart, sizeof(hstart), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+    hstart[NBUCKETS] = (int)rows;
+    for (int b = NBUCKETS - 1; b >= 0; b--) if (hstart[b] < 0) hstart[b] = hstart[b + 1];
+    CUDA_TRY(cudaEventRecord(ev[2], s));
+
+    int n_unsupported = 0;
+    for (int b = 0; b < NBUCKETS; b++) {
+        const int count = hstart[b + 1] - hstart[b];
+        if (count <= 0) continue;
+        const int *list = d->dIdxSorted + hstart[b];
+        if (b == 0) {
+            n_unsupported = count;
+            unsupported_kernel<<<(count + 255) / 256, 256, 0, s>>>(list, count, rp);
+        } else if (b == 1) {
+            gauss_kernel<<<(count + 127) / 128, 128, 0, s>>>(d->m, c, d->dDescs, d->dChild, list, count, rp);
+        } else {
+            const int code = b - 2, icpt = code & 1, fk = code >> 1, fam = fk / (MAXK + 1), k = fk % (MAXK + 1);
+            FitLaunchFn fn = nullptr;
+            if (fam == 0) fn = (c.method == MLE) ? get_launch_bin_mle(k, icpt) : get_launch_bin_bayes(k, icpt);
+            else if (fam == 1) fn = get_launch_pois(k, icpt);
+            if (!fn) {
+                n_unsupported += count;
+                unsupported_kernel<<<(count + 255) / 256, 256, 0, s>>>(list, count, rp);
+            } else {
+                const int warps_needed = count;
+                int grid = std::min((warps_needed + FIT_WARPS - 1) / FIT_WARPS, d->sm_count * 2);
+                fn(d->m, c, d->dDescs, d->dChild, list, count, d->dCounters + b, rp, grid, s);
+            }
+        }
+        launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ev[3], s));
+    if (out->mlik) CUDA_TRY(cudaMemcpyAsync(out->mlik, rp.mlik, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (ctrl->method == ABN_METHOD_MLE) {
+        if (out->aic) CUDA_TRY(cudaMemcpyAsync(out->aic, rp.aic, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (out->bic) CUDA_TRY(cudaMemcpyAsync(out->bic, rp.bic, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (out->mdl) CUDA_TRY(cudaMemcpyAsync(out->mdl, rp.mdl, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    if (out->status) CUDA_TRY(cudaMemcpyAsync(out->status, rp.status, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+    std::vector<int> iters_host;
+    int *iters_dst = out->iters;
+    if (!iters_dst) { iters_host.resize(rows); iters_dst = iters_host.data(); }
+    CUDA_TRY(cudaMemcpyAsync(iters_dst, rp.iters, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(ev[4], s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+
+    float ms[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    d->timing.h2d_ms = ms[0];
+    d->timing.plan_ms = ms[1];
+    d->timing.fit_ms = ms[2];
+    d->timing.d2h_ms = ms[3];
+    d->timing.launches = launches;
+    // algorithmic bytes: passes * n * (k_data + 1) * 8 per fit
+    long long bytes = 0;
+    for (long long r = 0; r < rows; r++) {
+        int kd = 0;
+        for (int j = 0; j < width; j++) {
+            const int p = cand->parents[r * width + j];
+            if (p >= 0) kd += d->col0[p + 1] - d->col0[p];
+        }
+        const int ch = cand->child[r];
+        const int yw = d->col0[ch + 1] - d->col0[ch];
+        bytes += (long long)iters_dst[r] * d->m.n * (kd + yw) * 8;
+    }
+    d->timing.algo_bytes = bytes;
+    if (n_unsupported > 0 && n_unsupported == rows)
+        return fail(err, errlen, ABN_ERR_LIMIT, "no candidate could be scored: designs wider than %d columns or multinomial children are not supported by this build", MAXK);
+    return ABN_OK;
+}
+
+extern "C" int abn_b200_score_cache(const abn_dataset *ds, const abn_candidates *cand, const abn_control *ctrl,
+                                    abn_result *out, char *err, size_t errlen)
+{
+    if (!ctrl) return fail(err, errlen, ABN_ERR_ARG, "null control");
+    abn_data *d = nullptr;
+    int rc = abn_b200_data_create(ds, ctrl->device, &d, err, errlen);
+    if (rc != ABN_OK) return rc;
+    rc = abn_b200_score(d, cand, ctrl, out, err, errlen);
+    abn_b200_data_destroy(d);
+    return rc;
+}
+
+extern "C" int abn_b200_last_timing(const abn_data *d, abn_timing *t)
+{
+    if (!d || !t) return ABN_ERR_ARG;
+    *t = d->timing;
+    return ABN_OK;
+}
+
+extern "C" int32_t abn_b200_version(void) { return ABN_B200_VERSION; }
+
+extern "C" int32_t abn_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void abn_b200_default_control(int32_t method, abn_control *c)
+{
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->method = method;
+    c->max_iters = 100;            // R/build_score_cache.R:97
+    c->tol = 1e-8;                 // :113
+    c->epsabs = 1e-7;              // :98
+    c->prior_mean = 0.0;           // :93
+    c->prior_sd = 1.0 / sqrt(0.001); // 1/sqrt(prec), :94 and _bayes.R:314
+    c->gam_shape = 1.0;            // :95
+    c->gam_scale = 1.0 / 5e-05;    // 1/loggam.inv.scale, :96 and _bayes.R:315
+    c->solver = ABN_SOLVER_HYBRID;
+    c->device = 0;
+    c->nvars = 0;
+}

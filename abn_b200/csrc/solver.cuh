@@ -25,7 +25,7 @@
 
 #if defined(__CUDACC__)
 #define ABN_HD __host__ __device__ __forceinline__
-#define ABN_HDN __host__ __device__ __noinline__
+#define ABN_HDN inline __host__ __device__ __noinline__
 #else
 #define ABN_HD inline
 #define ABN_HDN inline
@@ -657,12 +657,10 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
     case PH_POIS_TRIAL: {
         // a.H = X'WX, a.g = X'(y - W), a.ll = sum(y eta - exp(eta)) at s.x
         double ll_here = a.ll - s.lfact;
-        bool accepted_or_first = true;
         if (s.phase == PH_POIS_TRIAL) {
             // step-halving test at the trial point (irls_poisson_fast.cpp:98-120)
             bool acc = !a.bad && isfinite(ll_here) && ll_here >= s.cur_ll;
             if (!acc) {
-                accepted_or_first = false;
                 s.step *= 0.5;
                 s.halvings++;
                 if (s.halvings < 10) {
@@ -688,7 +686,6 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
             if (sqrt(nrm) < c.tol) { mle_scores(s, ll_here, (double)k); return PASS_DONE; } // final ll :137 at the same x
             if (s.iters >= c.max_iters) { s.status = FIT_NOT_CONVERGED; mle_scores(s, ll_here, (double)k); return PASS_DONE; }
         }
-        (void)accepted_or_first;
         // next IRLS iteration from s.x with this pass's sums (:62-91)
         if (s.phase == PH_POIS_FIRST && c.max_iters <= 0) { mle_scores(s, ll_here, (double)k); return PASS_DONE; }
         if (a.bad) { // non-finite weights -> break (:66-69); final ll at x is non-finite too

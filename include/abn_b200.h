@@ -82,7 +82,7 @@ enum {
     ABN_ERR_ALLOC = -5
 };
 
-#define ABN_MAX_K 16 /* widest design matrix (intercept + expanded parent columns) */
+#define ABN_MAX_K 8 /* widest design matrix (intercept + expanded parent columns) this build streams */
 
 /*
  * The data set, already prepared as the R drivers prepare it before their loops

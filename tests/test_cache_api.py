@@ -1,0 +1,67 @@
+"""Argument handling of the Python mirror of buildScoreCache / build.control (no GPU needed)."""
+import numpy as np
+import pytest
+
+from abn_b200 import cache as abncache
+from abn_b200 import synth
+
+
+def _data():
+    return synth.make_columns(40, ["gaussian", "binomial", "poisson", "binomial"], seed=11)
+
+
+def test_build_control_defaults():
+    b = abncache.build_control("bayes")
+    assert (b["mean"], b["prec"], b["loggam.shape"], b["loggam.inv.scale"], b["max.iters"], b["epsabs"]) == \
+        (0, 0.001, 1, 5e-05, 100, 1e-07)
+    m = abncache.build_control("mle", max_iters=50)
+    assert m["max.iters"] == 50 and m["tol"] == 1e-8 and "prec" not in m
+    with pytest.raises(ValueError):
+        abncache.build_control("foo")
+    with pytest.raises(TypeError):
+        abncache.build_control("mle", nonsense=1)
+
+
+def test_argument_validation():
+    names, data, dists = _data()
+    with pytest.raises(ValueError):
+        abncache.buildScoreCache(None, dists)
+    with pytest.raises(ValueError):
+        abncache.buildScoreCache(data, dists, method="xyz")
+    with pytest.raises(ValueError):
+        abncache.buildScoreCache(data, {k: v for k, v in list(dists.items())[:2]}, method="mle", max_parents=1)
+    ban = np.zeros((4, 4), int)
+    ret = np.zeros((4, 4), int)
+    ban[0, 1] = ret[0, 1] = 1
+    with pytest.raises(ValueError, match="inconsistent"):
+        abncache.buildScoreCache(data, dists, method="mle", max_parents=2, dag_banned=ban, dag_retained=ret)
+    ret2 = np.zeros((4, 4), int)
+    ret2[0, 1:] = 1
+    with pytest.raises(ValueError, match="max.parents"):
+        abncache.buildScoreCache(data, dists, method="mle", max_parents=1, dag_retained=ret2)
+    with pytest.raises(ValueError, match="own parent"):
+        abncache.buildScoreCache(data, dists, method="mle", max_parents=1, dag_banned=np.eye(4, dtype=int))
+    with pytest.raises(ValueError, match="ISSUE"):
+        abncache.buildScoreCache(data, dists, method="mle", max_parents={n: i % 2 + 1 for i, n in enumerate(names)})
+    with pytest.raises(NotImplementedError):
+        abncache.buildScoreCache(data, dists, method="mle", group_var="g1")
+    md = dict(dists)
+    md[names[1]] = "multinomial"
+    with pytest.raises(ValueError, match="Multinomial"):
+        abncache.buildScoreCache(data, md, method="bayes", max_parents=1)
+
+
+def test_dry_run_returns_node_definitions_without_a_gpu():
+    names, data, dists = _data()
+    with pytest.warns(UserWarning):
+        out = abncache.buildScoreCache(data, dists, method="bayes", max_parents=9, dry_run=True)
+    assert out["node.defn"].shape == (4 * 8, 4) and list(out["children"][:8]) == [1] * 8
+    out = abncache.buildScoreCache(data, dists, method="mle", max_parents=2, dry_run=True,
+                                   dag_banned="~g1|b1", dag_retained={"p1": ["g1"]})
+    nd, ch = out["node.defn"], out["children"]
+    assert not nd[(ch == 1), 1].any() and nd[(ch == 3), 0].all()
+
+
+def test_formula_parser():
+    m = abncache._parse_formula("~a|b:c+d|.", ["a", "b", "c", "d"])
+    assert m.tolist() == [[0, 1, 1, 0], [0, 0, 0, 0], [0, 0, 0, 0], [1, 1, 1, 0]]
