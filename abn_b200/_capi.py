@@ -18,6 +18,7 @@ METHOD_MLE, METHOD_BAYES = 0, 1
 SOLVER_NEWTON, SOLVER_HYBRID = 0, 1
 FIT_OK, FIT_NOT_CONVERGED, FIT_NON_FINITE = 0, 1, 2
 MAX_K = 8
+MAX_KERNELS = 64
 
 FAMILY_CODE = {"binomial": BINOMIAL, "gaussian": GAUSSIAN, "poisson": POISSON, "multinomial": MULTINOMIAL}
 
@@ -81,6 +82,12 @@ class Timing(C.Structure):
         ("d2h_ms", C.c_double),
         ("launches", C.c_int64),
         ("algo_bytes", C.c_int64),
+        ("n_kernels", C.c_int32),
+        ("reserved", C.c_int32),
+        ("kernel_id", C.c_int32 * MAX_KERNELS),
+        ("kernel_fits", C.c_int64 * MAX_KERNELS),
+        ("kernel_bytes", C.c_int64 * MAX_KERNELS),
+        ("kernel_ms", C.c_double * MAX_KERNELS),
     ]
 
 

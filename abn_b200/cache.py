@@ -208,6 +208,16 @@ def node_defn(children0, parents, d):
     return out
 
 
+def kernel_name(kid: int) -> str:
+    """Readable name of abn_timing.kernel_id."""
+    if kid == 1:
+        return "gauss_kernel"
+    code = kid - 2
+    icpt, fk = code & 1, code >> 1
+    fam, k = divmod(fk, capi.MAX_K + 1)
+    return f"fit_kernel<{('binomial', 'poisson', 'multinomial')[fam]},K={k},icpt={icpt}>"
+
+
 class DeviceData:
     """A data set resident on one GPU (``abn_b200_data_create``) that candidate lists can be scored
     against repeatedly (``abn_b200_score``)."""
@@ -232,7 +242,10 @@ class DeviceData:
     def timing(self) -> dict:
         t = capi.Timing()
         capi.lib().abn_b200_last_timing(self._h, C.byref(t))
-        return {k: getattr(t, k) for k, _ in capi.Timing._fields_}
+        out = {k: getattr(t, k) for k in ("h2d_ms", "plan_ms", "fit_ms", "d2h_ms", "launches", "algo_bytes")}
+        out["kernels"] = [{"id": t.kernel_id[i], "name": kernel_name(t.kernel_id[i]), "fits": t.kernel_fits[i],
+                           "bytes": t.kernel_bytes[i], "ms": t.kernel_ms[i]} for i in range(t.n_kernels)]
+        return out
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -43,6 +44,21 @@ static int fail(char *err, size_t errlen, int code, const char *fmt, ...)
             return fail(err, errlen, code_, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_),       \
                         __FILE__, __LINE__);                                                        \
         }                                                                                           \
+    } while (0)
+
+// ABN_B200_DEBUG_SYNC=1: synchronise and check after every launch, naming the step that failed
+static bool debug_sync()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("ABN_B200_DEBUG_SYNC"); v = (e && *e && *e != '0') ? 1 : 0; }
+    return v == 1;
+}
+#define KCHECK(what, stream)                                                                        \
+    do {                                                                                            \
+        cudaError_t e_ = cudaGetLastError();                                                        \
+        if (e_ == cudaSuccess && debug_sync()) { e_ = cudaStreamSynchronize(stream); if (e_ == cudaSuccess) e_ = cudaGetLastError(); } \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(err, errlen, ABN_ERR_CUDA, "%s: %s (%s:%d)", what, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
@@ -455,11 +471,14 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     const int tb = 128;
     resolve_kernel<<<(unsigned)((rows + tb - 1) / tb), tb, 0, s>>>(d->m, c.method, rows, width, d->dChild, d->dParents,
                                                                   d->dDescs, d->dKeys, d->dIdx);
+    KCHECK("resolve_kernel", s);
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(d->dSortTmp, d->sortTmpBytes, d->dKeys, d->dKeysSorted, d->dIdx, d->dIdxSorted,
                                              (int)rows, 0, 8, s));
     CUDA_TRY(cudaMemsetAsync(d->dBucketStart, 0xff, (size_t)(NBUCKETS + 1) * sizeof(int), s));
     CUDA_TRY(cudaMemsetAsync(d->dCounters, 0, (size_t)(NBUCKETS + 1) * sizeof(int), s));
+    KCHECK("radix sort", s);
     bucket_bounds<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(d->dKeysSorted, rows, d->dBucketStart);
+    KCHECK("bucket_bounds", s);
     launches += 3;
     int hstart[NBUCKETS + 1];
     CUDA_TRY(cudaMemcpyAsync(hstart, d->dBucketStart, sizeof(hstart), cudaMemcpyDeviceToHost, s));
@@ -470,9 +489,20 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     CUDA_TRY(cudaEventRecord(ev[2], s));
 
     int n_unsupported = 0;
+    std::vector<cudaEvent_t> kev;
+    std::vector<int> kid, kcount, kstart;
     for (int b = 0; b < NBUCKETS; b++) {
         const int count = hstart[b + 1] - hstart[b];
         if (count <= 0) continue;
+        if (b >= 1 && (int)kid.size() < ABN_MAX_KERNELS) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreate(&e));
+            CUDA_TRY(cudaEventRecord(e, s));
+            kev.push_back(e);
+            kid.push_back(b);
+            kcount.push_back(count);
+            kstart.push_back(hstart[b]);
+        }
         const int *list = d->dIdxSorted + hstart[b];
         if (b == 0) {
             n_unsupported = count;
@@ -493,10 +523,17 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
                 fn(d->m, c, d->dDescs, d->dChild, list, count, d->dCounters + b, rp, grid, s);
             }
         }
+        {
+            char what[64];
+            snprintf(what, sizeof(what), "fit kernel bucket %d (%d fits)", b, count);
+            KCHECK(what, s);
+        }
         launches++;
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev[3], s));
+    std::vector<int> sorted_rows(rows);
+    CUDA_TRY(cudaMemcpyAsync(sorted_rows.data(), d->dIdxSorted, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (out->mlik) CUDA_TRY(cudaMemcpyAsync(out->mlik, rp.mlik, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (ctrl->method == ABN_METHOD_MLE) {
         if (out->aic) CUDA_TRY(cudaMemcpyAsync(out->aic, rp.aic, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -514,15 +551,13 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
 
     float ms[4] = {0, 0, 0, 0};
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
-    for (auto &e : ev) cudaEventDestroy(e);
     d->timing.h2d_ms = ms[0];
     d->timing.plan_ms = ms[1];
     d->timing.fit_ms = ms[2];
     d->timing.d2h_ms = ms[3];
     d->timing.launches = launches;
     // algorithmic bytes: passes * n * (k_data + 1) * 8 per fit
-    long long bytes = 0;
-    for (long long r = 0; r < rows; r++) {
+    auto fit_bytes = [&](long long r) {
         int kd = 0;
         for (int j = 0; j < width; j++) {
             const int p = cand->parents[r * width + j];
@@ -530,9 +565,24 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
         }
         const int ch = cand->child[r];
         const int yw = d->col0[ch + 1] - d->col0[ch];
-        bytes += (long long)iters_dst[r] * d->m.n * (kd + yw) * 8;
-    }
+        return (long long)iters_dst[r] * d->m.n * (kd + yw) * 8;
+    };
+    long long bytes = 0;
+    for (long long r = 0; r < rows; r++) bytes += fit_bytes(r);
     d->timing.algo_bytes = bytes;
+    d->timing.n_kernels = (int)kid.size();
+    for (size_t i = 0; i < kid.size(); i++) {
+        float kms = 0;
+        cudaEventElapsedTime(&kms, kev[i], i + 1 < kid.size() ? kev[i + 1] : ev[3]);
+        long long kb = 0;
+        for (int t = 0; t < kcount[i]; t++) kb += fit_bytes(sorted_rows[kstart[i] + t]);
+        d->timing.kernel_id[i] = kid[i];
+        d->timing.kernel_fits[i] = kcount[i];
+        d->timing.kernel_bytes[i] = kb;
+        d->timing.kernel_ms[i] = kms;
+    }
+    for (auto &e : kev) cudaEventDestroy(e);
+    for (auto &e : ev) cudaEventDestroy(e);
     if (n_unsupported > 0 && n_unsupported == rows)
         return fail(err, errlen, ABN_ERR_LIMIT, "no candidate could be scored: designs wider than %d columns or multinomial children are not supported by this build", MAXK);
     return ABN_OK;

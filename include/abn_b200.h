@@ -184,8 +184,10 @@ int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn_control *c
 int abn_b200_score_cache(const abn_dataset *ds, const abn_candidates *cand,
                          const abn_control *ctrl, abn_result *out, char *err, size_t errlen);
 
-/* instrumentation of the last abn_b200_score on this handle: device milliseconds by phase and
- * kernel launches issued (bench.py's gpu_launches). Any pointer may be NULL. */
+/* instrumentation of the last abn_b200_score on this handle: device milliseconds by phase (CUDA
+ * events on the library's stream), kernel launches issued (bench.py's gpu_launches) and, per fit
+ * kernel launched, its duration, fits and algorithmic bytes. */
+#define ABN_MAX_KERNELS 64
 typedef struct abn_timing {
     double h2d_ms;      /* candidate upload                                                  */
     double plan_ms;     /* design resolution / rank / work-list build                        */
@@ -193,6 +195,14 @@ typedef struct abn_timing {
     double d2h_ms;      /* result download                                                   */
     int64_t launches;   /* kernels launched                                                  */
     int64_t algo_bytes; /* sum over fits of passes * n * (k_data + 1) * 8         */
+    int32_t n_kernels;  /* fit kernels launched by the call, entries used below              */
+    int32_t reserved;
+    int32_t kernel_id[ABN_MAX_KERNELS];    /* 1 = Gram-only Gaussian kernel; otherwise
+                                              2 + ((family_idx * (ABN_MAX_K+1) + k) * 2 + intercept),
+                                              family_idx 0 = binomial, 1 = Poisson            */
+    int64_t kernel_fits[ABN_MAX_KERNELS];
+    int64_t kernel_bytes[ABN_MAX_KERNELS]; /* algorithmic bytes of the fits that kernel ran  */
+    double kernel_ms[ABN_MAX_KERNELS];
 } abn_timing;
 int abn_b200_last_timing(const abn_data *d, abn_timing *t);
 
