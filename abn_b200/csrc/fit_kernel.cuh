@@ -36,15 +36,15 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// one pass of one fit by one warp. MODE is PASS_FULL / PASS_GRAD / PASS_HESS.
+// one pass of one fit by one warp. MODE is PASS_FULL / PASS_HG / PASS_GRAD / PASS_HESS / PASS_LL.
 template <int KIND, int K, bool ICPT, int MODE>
 __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const double *const (&cp)[MAXK],
                                           const double *beta_sm, long long n, const RowConst rc, PassAcc *acc_sm)
 {
     constexpr int KD = K - (ICPT ? 1 : 0); // streamed design columns
-    constexpr bool NEED_H = (MODE != PASS_GRAD);
-    constexpr bool NEED_G = (MODE != PASS_HESS);
-    constexpr bool NEED_L = (MODE == PASS_FULL);
+    constexpr bool NEED_H = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_HESS);
+    constexpr bool NEED_G = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_GRAD);
+    constexpr bool NEED_L = (MODE == PASS_FULL || MODE == PASS_LL);
     const int lane = threadIdx.x & 31;
 
     double beta[K];
@@ -71,7 +71,7 @@ __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const do
 #pragma unroll
         for (int j = (ICPT ? 1 : 0); j < K; j++) eta = fma(x[j], beta[j], eta);
         double w, r, l = 0.0;
-        RowOp<KIND>::template apply<NEED_L>(eta, yi, rc, w, r, l, bad);
+        RowOp<KIND>::template apply<NEED_H, NEED_G, NEED_L>(eta, yi, rc, w, r, l, bad);
         if (NEED_H) {
             int t = 0;
 #pragma unroll
@@ -124,6 +124,9 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
 {
     __shared__ FitState st_all[FIT_WARPS];
     __shared__ PassAcc acc_all[FIT_WARPS];
+    __shared__ double exp_tab[32];
+    if (threadIdx.x < 32) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FitState &st = st_all[warp];
     PassAcc *acc = &acc_all[warp];
@@ -145,7 +148,7 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
             cp[j] = m.X + (long long)(col < 0 ? 0 : col) * m.ld;
         }
         const double *y = m.X + (long long)d.ycol * m.ld;
-        const RowConst rc = make_row_const(K, (double)m.n);
+        const RowConst rc = make_row_const(K, (double)m.n, exp_tab);
 
         int mode = 0;
         if (lane == 0) {
@@ -156,10 +159,13 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
         mode = __shfl_sync(0xffffffffu, mode, 0);
         __syncwarp();
         while (mode != PASS_DONE) {
-            if (mode == PASS_FULL) warp_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc);
-            else if (mode == PASS_GRAD) warp_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc);
-            else if (mode == PASS_HESS) warp_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc);
-            else warp_pass<RK_PINIT, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc);
+            // only the modes a row kind's state machines can ask for are instantiated
+            if (mode == PASS_HG) warp_pass<KIND, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc);
+            else if (mode == PASS_FULL) warp_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc);
+            else if (mode == PASS_LL) warp_pass<KIND, K, ICPT, PASS_LL>(y, cp, st.x, m.n, rc, acc);
+            else if (KIND != RK_BIN_MLE && mode == PASS_GRAD) warp_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc);
+            else if (KIND != RK_BIN_MLE && mode == PASS_HESS) warp_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc);
+            else if (KIND == RK_POIS && mode == PASS_PINIT) warp_pass<RK_PINIT, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc);
             __syncwarp();
             if (lane == 0) mode = fit_consume(st, c, *acc);
             mode = __shfl_sync(0xffffffffu, mode, 0);

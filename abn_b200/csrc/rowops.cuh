@@ -4,8 +4,11 @@
 //
 // One struct per (family, method); all FP64. Reference formulas (paths relative to the
 // reference tree) are cited per op. __host__ __device__ so tests/host_sim.cpp reuses them.
+// Each op is templated on what the pass needs (NEED_W: Hessian weight, NEED_R: score residual,
+// NEED_L: log-likelihood term) so a gradient-only or loglik-only pass does not pay for the rest.
 #pragma once
 
+#include "fastmath.cuh"
 #include "solver.cuh"
 
 namespace abn {
@@ -18,18 +21,22 @@ enum RowKind : int {
 };
 
 struct RowConst {
-    double bp0, bp1; // binomial MLE bias-reduced pseudo-responses for y = 0 / y = 1
+    double bp0, bp1;   // binomial MLE bias-reduced pseudo-responses for y = 0 / y = 1 (b' = bp0 + y (bp1 - bp0))
+    const double *tab; // 2^(j/32) table for fast_exp (shared memory on the device)
 };
 
 // b' = (y + 0.5 k/n) / (1 + k/n), irls_binomial_fast_br.cpp:58
-ABN_HD RowConst make_row_const(int k, double n)
+ABN_HD RowConst make_row_const(int k, double n, const double *tab)
 {
     RowConst c;
     double dfn = (double)k / n;
     c.bp0 = (0.0 + dfn * 0.5) / (1 + dfn);
     c.bp1 = (1.0 + dfn * 0.5) / (1 + dfn);
+    c.tab = tab;
     return c;
 }
+
+ABN_HD double clamp700(double t) { return fmin(fmax(t, -700.0), 700.0); }
 
 template <int KIND>
 struct RowOp;
@@ -43,54 +50,59 @@ struct RowOp<RK_BIN_MLE> {
     // that noise moves the fixed point of the reference's IRLS at the 1e-8 level; parity needs
     // the same rho. So: W = rho g', W z = W eta + rho (b' - g), i.e. the Newton form
     //   x_new = x + (X'WX)^-1 X'[rho (b' - g)]  ==  solve(X'WX, X'Wz)  (irls_binomial_fast_br.cpp:72-73)
+    // with g = fl(1/(1+e)) correctly rounded like the reference's division.
     // loglik term: -y log(1+e^-eta) - (1-y) log(1+e^eta) = -log(1+e) - (1-y) eta   (:97)
-    template <bool NEED_L>
+    template <bool NEED_W, bool NEED_R, bool NEED_L>
     static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad)
     {
-        double e = exp(-eta);
-        double d = 1.0 + e;
-        double g = 1.0 / d;          // IEEE division: the same g as the reference's
-        double gp = e * g * g;
-        double rho = gp / (g * (1.0 - g));
-        w = rho * gp;
-        r = rho * (((y != 0.0) ? c.bp1 : c.bp0) - g);
-        // the reference's W or z is non-finite when g rounds to 1 (g(1-g) = 0) or (1+e)^2 overflows
-        bad |= (d == 1.0) | !(d < 1.3407807929942596e154);
+        // The reference's W or z is non-finite when g rounds to 1 (g(1-g) = 0: 1 + e == 1, i.e.
+        // eta >= 53 ln 2) or when (1+e)^2 overflows (e >= sqrt(DBL_MAX), eta <= -354.89). Outside
+        // that window the fit is flagged and whatever fast_exp returns is never used; inside it
+        // fast_exp needs no range clamp.
+        bad |= !((eta < 36.7368005696771) & (eta > -354.891356446692));
+        const double e = fast_exp(-eta, c.tab);
+        const double d = 1.0 + e;
+        if (NEED_W || NEED_R) {
+            const double g = fast_rcp(d);
+            const double gp = e * g * g;
+            const double rho = gp * fast_rcp_approx(g * (1.0 - g));
+            w = rho * gp;
+            r = rho * (fma(y, c.bp1 - c.bp0, c.bp0) - g);
+        }
         if (NEED_L) l = -log(d) - (1.0 - y) * eta;
     }
 };
 
 template <>
 struct RowOp<RK_POIS> {
-    template <bool NEED_L>
-    static ABN_HD void apply(double eta, double y, const RowConst &, double &w, double &r, double &l, int &bad)
+    template <bool NEED_W, bool NEED_R, bool NEED_L>
+    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad)
     {
-        double E = exp(eta);
+        bad |= !(eta < 709.782712893384); // exp(eta) = +Inf (or eta is NaN) in the reference
+        const double E = fast_exp(fmax(eta, -700.0), c.tab); // flagged fits never use E; no upper clamp
         w = E;
         r = y - E;
-        bad |= !isfinite(E);
-        if (NEED_L) l = y * eta - E;
+        if (NEED_L) l = fma(y, eta, -E);
     }
 };
 
 template <>
 struct RowOp<RK_BIN_BAYES> {
-    template <bool NEED_L>
-    static ABN_HD void apply(double eta, double y, const RowConst &, double &w, double &r, double &l, int &bad)
+    // E = exp(eta): sigma = E/(1+E) (1 if E overflows, node_binomial.c:697-700),
+    // hessian weight exp(eta - 2 log(1+E)) = sigma/(1+E) (:761-764), log term log(1+E) (eta if E
+    // overflows, :633-639). For |eta| > 700 the clamped E gives the same doubles as those branches.
+    template <bool NEED_W, bool NEED_R, bool NEED_L>
+    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad)
     {
-        double E = exp(eta);
-        if (E != INFINITY) {
-            double d = 1.0 + E;
-            double inv = 1.0 / d;
-            double sig = E * inv;
-            w = sig * inv;          // exp(eta - 2 log(1+e^eta)), node_binomial.c:761-764
-            r = y - sig;            // :697-700
-            if (NEED_L) l = y * eta - log(d); // :633-639
-        } else {
-            w = 0.0;
-            r = y - 1.0;
-            if (NEED_L) l = y * eta - eta;
+        const double E = fast_exp(clamp700(eta), c.tab);
+        const double d = 1.0 + E;
+        if (NEED_W || NEED_R) {
+            const double inv = fast_rcp_approx(d);
+            const double sig = E * inv;
+            w = sig * inv;
+            r = y - sig;
         }
+        if (NEED_L) l = (eta > 700.0) ? (y * eta - eta) : (y * eta - log(d));
         (void)bad;
     }
 };
@@ -98,7 +110,7 @@ struct RowOp<RK_BIN_BAYES> {
 template <>
 struct RowOp<RK_PINIT> {
     // mu = y + 0.1; eta0 = log(mu); W0 = exp(eta0); z0 = eta0 + (y - W0)/W0; H = X'W0X, g = X'W0z0
-    template <bool NEED_L>
+    template <bool NEED_W, bool NEED_R, bool NEED_L>
     static ABN_HD void apply(double, double y, const RowConst &, double &w, double &r, double &l, int &bad)
     {
         double mu = y + 0.1;

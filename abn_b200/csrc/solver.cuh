@@ -48,7 +48,9 @@ enum PassMode : int {
     PASS_FULL = 1,   // H, g, ll at state.x
     PASS_GRAD = 2,   // g only (hybrid trial points)
     PASS_HESS = 3,   // H only (hybrid Jacobian refresh)
-    PASS_PINIT = 4   // Poisson MLE start values: H = X'W0X, g = X'W0z0 (irls_poisson_fast.cpp:37-52)
+    PASS_PINIT = 4,  // Poisson MLE start values: H = X'W0X, g = X'W0z0 (irls_poisson_fast.cpp:37-52)
+    PASS_HG = 5,     // H and g, no log-likelihood term (saves the log per row)
+    PASS_LL = 6      // log-likelihood term only
 };
 
 struct Control {
@@ -329,7 +331,7 @@ ABN_HD double scaled_enorm(const double *d, const double *f, int n)
 // fit state
 // ------------------------------------------------------------------------------------------------
 enum Phase : int {
-    PH_MLE_BIN = 1,
+    PH_MLE_BIN = 1, PH_MLE_BIN_LL, PH_FINAL_LL,
     PH_POIS_INIT, PH_POIS_FIRST, PH_POIS_TRIAL,
     PH_NEWTON,
     PH_HYB_SET, PH_HYB_TRIAL, PH_HYB_JAC, PH_FINAL
@@ -346,6 +348,7 @@ struct FitState {
     double x[MAXM];
     // bookkeeping
     int phase, iters, passes, status;
+    int have_ll;      // the pass in flight also produces the log-likelihood term
     // results
     double loglik, aic, bic;
     // MLE Poisson
@@ -445,11 +448,9 @@ ABN_HD void bayes_eval(const FitState &s, const Control &c, const double *x, con
     if (gval) *gval = bayes_g_from_acc(s, c, x, a);
 }
 
-// node_binomial.c:172-193: Laplace score at x from g and hess g
-ABN_HDN void bayes_finish(FitState &s, const Control &c, const PassAcc &a)
+// node_binomial.c:172-193: Laplace score from g(x) and hess g(x) (in s.J, destroyed)
+ABN_HDN void bayes_score(FitState &s, double gval)
 {
-    double gval;
-    bayes_eval(s, c, s.x, a, nullptr, s.J, &gval);
     int perm[MAXM];
     lu_decomp(s.J, s.M, perm);
     double mydet = lu_lndet(s.J, s.M);
@@ -458,6 +459,14 @@ ABN_HDN void bayes_finish(FitState &s, const Control &c, const PassAcc &a)
     if (isnan(score)) { score = NAN; s.status = FIT_NON_FINITE; }
     s.loglik = score;
     s.aic = s.bic = NAN;
+}
+
+// ... from a pass that produced H, g and ll at s.x
+ABN_HDN void bayes_finish(FitState &s, const Control &c, const PassAcc &a)
+{
+    double gval;
+    bayes_eval(s, c, s.x, a, nullptr, s.J, &gval);
+    bayes_score(s, gval);
 }
 
 // ---- Powell hybrid (GSL hybridj.c / dogleg.c) ---------------------------------------------------
@@ -535,7 +544,7 @@ ABN_HD int hy_start_attempt(FitState &s)
     s.scale = hy_attempt_scale(s, s.attempt, &valid) ? 1 : 0;
     for (int i = 0; i < s.M; i++) { s.xc[i] = s.x0[i]; s.x[i] = s.x0[i]; }
     s.phase = PH_HYB_SET;
-    return PASS_FULL;
+    return PASS_HG;
 }
 
 // the trial point of the next hybrid iteration: dogleg step from (xc, f, Q, R)
@@ -590,7 +599,8 @@ ABN_HDN int fit_begin(FitState &s, const Control &c)
         if (s.family == BINOMIAL) {
             for (int i = 0; i < s.k; i++) s.x[i] = 0.0; // x.zeros, irls_binomial_fast_br.cpp:19
             s.phase = PH_MLE_BIN;
-            return PASS_FULL;
+            s.have_ll = (c.max_iters <= 1);
+            return s.have_ll ? PASS_FULL : PASS_HG;
         }
         s.phase = PH_POIS_INIT;
         return PASS_PINIT;
@@ -598,7 +608,7 @@ ABN_HDN int fit_begin(FitState &s, const Control &c)
     if (c.solver == HYBRID) return hy_start_attempt(s);
     for (int i = 0; i < s.M; i++) s.x[i] = s.x0[i];
     s.phase = PH_NEWTON;
-    return PASS_FULL;
+    return PASS_HG;
 }
 
 ABN_HD void mle_scores(FitState &s, double ll, double df)
@@ -621,7 +631,11 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
     const int k = s.k, M = s.M;
     switch (s.phase) {
     case PH_MLE_BIN: {
-        // a.g = X'(b' - g), a.H = X'WX, a.ll = loglik at s.x   (irls_binomial_fast_br.cpp:51-97)
+        // a.g = X'[rho (b' - g)], a.H = X'WX at s.x (irls_binomial_fast_br.cpp:51-73); a.ll = loglik at
+        // s.x when this pass was asked to produce it. The reported loglik is the one at the
+        // coefficients BEFORE the last update (:51,:97): it is computed in the pass that detects
+        // convergence when the previous step predicted it (quadratic convergence), otherwise in one
+        // extra loglik-only pass at the same point - identical value either way.
         s.iters++;
         double step[MAXM];
         unpack_sym(a, k, s.J);
@@ -632,10 +646,24 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
             return PASS_DONE;
         }
         double nrm = 0.0;
-        for (int i = 0; i < k; i++) { s.x[i] += step[i]; nrm += step[i] * step[i]; }
-        if (sqrt(nrm) < c.tol) { mle_scores(s, a.ll, (double)k); return PASS_DONE; } // :81, :97
-        if (s.iters >= c.max_iters) { s.status = FIT_NOT_CONVERGED; mle_scores(s, a.ll, (double)k); return PASS_DONE; }
-        return PASS_FULL;
+        for (int i = 0; i < k; i++) { s.xold[i] = s.x[i]; s.x[i] += step[i]; nrm += step[i] * step[i]; }
+        nrm = sqrt(nrm);
+        const bool converged = nrm < c.tol;                       // :81
+        if (converged || s.iters >= c.max_iters) {
+            if (!converged) s.status = FIT_NOT_CONVERGED;
+            if (s.have_ll) { mle_scores(s, a.ll, (double)k); return PASS_DONE; }
+            for (int i = 0; i < k; i++) s.x[i] = s.xold[i];
+            s.phase = PH_MLE_BIN_LL;
+            return PASS_LL;
+        }
+        s.have_ll = (nrm < 1e-4) || (s.iters + 1 >= c.max_iters);
+        return s.have_ll ? PASS_FULL : PASS_HG;
+    }
+    case PH_MLE_BIN_LL: {
+        const int keep = s.status;
+        mle_scores(s, a.ll, (double)k);
+        if (s.status == FIT_OK) s.status = keep;
+        return PASS_DONE;
     }
     case PH_POIS_INIT: {
         // irls_poisson_fast.cpp:37-58
@@ -729,22 +757,28 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
         double res = 0;
         bool fin = true;
         for (int i = 0; i < M; i++) { res += fabs(f[i]); if (!isfinite(f[i])) fin = false; }
-        if (res < c.epsabs) { s.status = FIT_OK; bayes_finish(s, c, a); return PASS_DONE; }
-        bool stop = (s.iters >= c.max_iters) || !fin;
-        if (!stop) {
+        if (res < c.epsabs) { s.status = FIT_OK; }
+        else if ((s.iters >= c.max_iters) || !fin) { s.status = FIT_NOT_CONVERGED; }
+        else {
             int perm[MAXM];
             for (int i = 0; i < M * MAXM; i++) s.Q[i] = s.J[i];
             lu_decomp(s.Q, M, perm);
-            if (lu_singular(s.Q, M)) stop = true;
+            if (lu_singular(s.Q, M)) { s.status = FIT_NOT_CONVERGED; }
             else {
                 lu_solve(s.Q, perm, M, f, step);
                 for (int i = 0; i < M; i++) s.x[i] -= step[i];
                 s.iters++;
-                return PASS_FULL;
+                return PASS_HG;
             }
         }
-        s.status = FIT_NOT_CONVERGED;
-        bayes_finish(s, c, a);
+        // g(x) is still missing: one loglik-only pass at the same point, hess g(x) stays in s.J
+        s.phase = PH_FINAL_LL;
+        return PASS_LL;
+    }
+    case PH_FINAL_LL: {
+        double gval;
+        bayes_eval(s, c, s.x, a, nullptr, nullptr, &gval);
+        bayes_score(s, gval);
         return PASS_DONE;
     }
     case PH_HYB_SET: {

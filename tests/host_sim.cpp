@@ -23,29 +23,34 @@ void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode
 {
     const int k = d.k;
     std::memset(&a, 0, sizeof(a));
-    RowConst rc = make_row_const(k, (double)m.n);
+    RowConst rc = make_row_const(k, (double)m.n, h_exp2_table);
     const double *y = m.X + (size_t)d.ycol * m.ld;
+    const bool need_h = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_HESS);
+    const bool need_g = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_GRAD);
+    const bool need_l = (mode == PASS_FULL || mode == PASS_LL);
     double x[MAXK];
     for (long long i = 0; i < m.n; i++) {
         double eta = 0.0;
         for (int j = 0; j < k; j++) {
             x[j] = d.cols[j] < 0 ? 1.0 : m.X[(size_t)d.cols[j] * m.ld + i];
-            eta += x[j] * beta[j];
+            eta = std::fma(x[j], beta[j], eta);
         }
-        double w, r, l = 0.0;
-        RowOp<KIND>::template apply<true>(eta, y[i], rc, w, r, l, a.bad);
-        if (mode != PASS_GRAD)
+        double w = 0.0, r = 0.0, l = 0.0;
+        if (need_l && (need_h || need_g)) RowOp<KIND>::template apply<true, true, true>(eta, y[i], rc, w, r, l, a.bad);
+        else if (need_l) RowOp<KIND>::template apply<false, false, true>(eta, y[i], rc, w, r, l, a.bad);
+        else RowOp<KIND>::template apply<true, true, false>(eta, y[i], rc, w, r, l, a.bad);
+        if (need_h)
             for (int p = 0; p < k; p++)
                 for (int q = p; q < k; q++) a.H[tri(p, q, k)] += w * x[p] * x[q];
-        if (mode != PASS_HESS)
+        if (need_g)
             for (int p = 0; p < k; p++) a.g[p] += r * x[p];
-        a.ll += l;
+        if (need_l) a.ll += l;
     }
 }
 
 void run_pass(const DataMeta &m, const FitDesc &d, const Control &c, const FitState &s, int mode, PassAcc &a)
 {
-    if (mode == PASS_PINIT) { host_pass<RK_PINIT>(m, d, s.x, PASS_FULL, a); return; }
+    if (mode == PASS_PINIT) { host_pass<RK_PINIT>(m, d, s.x, PASS_HG, a); return; }
     if (d.family == POISSON) { host_pass<RK_POIS>(m, d, s.x, mode, a); return; }
     if (c.method == MLE) host_pass<RK_BIN_MLE>(m, d, s.x, mode, a);
     else host_pass<RK_BIN_BAYES>(m, d, s.x, mode, a);
@@ -123,4 +128,10 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
         if (out->iters) out->iters[r] = passes;
     }
     return 0;
+}
+
+// fast FP64 math of the kernels (fastmath.cuh), host build, for tests/test_fastmath.py
+extern "C" void sim_fast_exp(const double *t, double *out, long n)
+{
+    for (long i = 0; i < n; i++) out[i] = fast_exp(t[i], h_exp2_table);
 }

@@ -1,0 +1,33 @@
+"""Accuracy of the branch-free exp the streaming kernels use (abn_b200/csrc/fastmath.cuh), host build."""
+import ctypes as C
+import math
+
+import numpy as np
+
+import helpers as H
+
+
+def _fast_exp(t):
+    lib = H.sim_lib()
+    lib.sim_fast_exp.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_long]
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    out = np.empty_like(t)
+    lib.sim_fast_exp(t.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)), len(t))
+    return out
+
+
+def test_fast_exp_about_one_ulp_over_the_working_range():
+    rng = np.random.default_rng(0)
+    t = np.concatenate([rng.uniform(-700, 700, 200_000), rng.uniform(-40, 40, 200_000), rng.normal(0, 2, 200_000),
+                        np.array([0.0, -0.0, 1e-300, -1e-300, 700.0, -700.0, 36.7368005696771, -354.891356446692])])
+    got = _fast_exp(t)
+    ref = np.exp(t.astype(np.longdouble))
+    ulp = np.spacing(np.exp(t))
+    err = np.abs((got.astype(np.longdouble) - ref) / ulp.astype(np.longdouble)).astype(np.float64)
+    assert err.max() < 1.05, err.max()      # table entry rounding (0.5 ulp) + final fma (0.5 ulp)
+    assert np.mean(err) < 0.35
+
+
+def test_fast_exp_exact_points():
+    got = _fast_exp(np.array([0.0, math.log(2.0) * 0]))
+    assert got[0] == 1.0
