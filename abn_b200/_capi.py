@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libabn_b200.so")
+# ABN_B200_LIB lets tuning sweeps point at a differently built copy of the same library
+LIB_PATH = os.environ.get("ABN_B200_LIB") or os.path.join(_HERE, "csrc", "libabn_b200.so")
 
 BINOMIAL, GAUSSIAN, POISSON, MULTINOMIAL = 1, 2, 3, 4
 METHOD_MLE, METHOD_BAYES = 0, 1

@@ -14,10 +14,12 @@
 
 #include "../../include/abn_b200.h"
 #include "fit_kernel.cuh"
+#include "fit_mn_kernel.cuh"
 
 using namespace abn;
 
 static_assert(ABN_MAX_K == MAXK, "include/abn_b200.h and solver.cuh disagree on the design width");
+static_assert(MN_MAXL == MN_MAXL_, "plan.cuh and solver_mn.cuh disagree on the multinomial level limit");
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing
@@ -182,7 +184,7 @@ __global__ void resolve_kernel(const DataMeta m, int method, long long rows, int
     if (r >= rows) return;
     FitDesc d;
     resolve_design(m, method, child[r], parents + r * width, width, d);
-    if (d.k == 0 || d.family == MULTINOMIAL) d.err = d.err ? d.err : 2;
+    if (d.k == 0 || (d.family == MULTINOMIAL && (d.nlev < 2 || d.nlev > MN_MAXL || method != MLE))) d.err = d.err ? d.err : 2;
     descs[r] = d;
     keys[r] = (unsigned char)bucket_of(d);
     idx[r] = (int)r;
@@ -256,6 +258,8 @@ struct abn_data {
     std::vector<int> family, col0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    static constexpr int NSIDE = 3;
+    cudaStream_t side[NSIDE] = {nullptr, nullptr, nullptr}; // small buckets run beside the large ones
     abn_timing timing{};
     // scratch that grows with the largest candidate list seen
     long long cap_rows = 0;
@@ -287,6 +291,7 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
     cudaFree(d->dX); cudaFree(d->dG); cudaFree(d->dLfact); cudaFree(d->dFamily); cudaFree(d->dCol0);
     cudaFree(d->dBucketStart); cudaFree(d->dCounters);
     if (d->stream) cudaStreamDestroy(d->stream);
+    for (auto &ss : d->side) if (ss) cudaStreamDestroy(ss);
     delete d;
 }
 
@@ -371,6 +376,7 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
         }                                                                       \
     } while (0)
     TRY_OR_FREE(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    for (auto &ss : d->side) TRY_OR_FREE(cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking));
     TRY_OR_FREE(cudaMalloc(&d->dX, (size_t)ld * ds->n_cols * sizeof(double)));
     TRY_OR_FREE(cudaMalloc(&d->dG, (size_t)D * D * sizeof(double)));
     TRY_OR_FREE(cudaMalloc(&d->dLfact, (size_t)ds->n_nodes * sizeof(double)));
@@ -489,47 +495,80 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     CUDA_TRY(cudaEventRecord(ev[2], s));
 
     int n_unsupported = 0;
-    std::vector<cudaEvent_t> kev;
+    // Launch order: buckets too small to fill the GPU go first, on side streams, so that they run in
+    // the gaps of the large ones (each large kernel is a persistent grid that drains its own queue);
+    // the large buckets follow on the main stream in cache order. Per-kernel CUDA events are recorded
+    // on the stream the kernel runs on.
+    std::vector<cudaEvent_t> kev0, kev1;
     std::vector<int> kid, kcount, kstart;
-    for (int b = 0; b < NBUCKETS; b++) {
-        const int count = hstart[b + 1] - hstart[b];
-        if (count <= 0) continue;
-        if (b >= 1 && (int)kid.size() < ABN_MAX_KERNELS) {
-            cudaEvent_t e;
-            CUDA_TRY(cudaEventCreate(&e));
-            CUDA_TRY(cudaEventRecord(e, s));
-            kev.push_back(e);
-            kid.push_back(b);
-            kcount.push_back(count);
-            kstart.push_back(hstart[b]);
-        }
-        const int *list = d->dIdxSorted + hstart[b];
-        if (b == 0) {
-            n_unsupported = count;
-            unsupported_kernel<<<(count + 255) / 256, 256, 0, s>>>(list, count, rp);
-        } else if (b == 1) {
-            gauss_kernel<<<(count + 127) / 128, 128, 0, s>>>(d->m, c, d->dDescs, d->dChild, list, count, rp);
-        } else {
-            const int code = b - 2, icpt = code & 1, fk = code >> 1, fam = fk / (MAXK + 1), k = fk % (MAXK + 1);
-            FitLaunchFn fn = nullptr;
-            if (fam == 0) fn = (c.method == MLE) ? get_launch_bin_mle(k, icpt) : get_launch_bin_bayes(k, icpt);
-            else if (fam == 1) fn = get_launch_pois(k, icpt);
-            if (!fn) {
-                n_unsupported += count;
-                unsupported_kernel<<<(count + 255) / 256, 256, 0, s>>>(list, count, rp);
-            } else {
-                const int warps_needed = count;
-                int grid = std::min((warps_needed + FIT_WARPS - 1) / FIT_WARPS, d->sm_count * 2);
-                fn(d->m, c, d->dDescs, d->dChild, list, count, d->dCounters + b, rp, grid, s);
+    const int small_limit = d->sm_count * ABN_MIN_BLOCKS * FIT_WARPS * 2;
+    cudaEvent_t planned;
+    CUDA_TRY(cudaEventCreateWithFlags(&planned, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(planned, s));
+    for (auto &ss : d->side) CUDA_TRY(cudaStreamWaitEvent(ss, planned, 0));
+    int n_side = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int b = 0; b < NBUCKETS; b++) {
+            const int count = hstart[b + 1] - hstart[b];
+            if (count <= 0) continue;
+            const bool small = (b >= 2) && count < small_limit;
+            if ((pass == 0) != small) continue;
+            cudaStream_t ks = small ? d->side[n_side++ % abn_data::NSIDE] : s;
+            const bool timed = (b >= 1 && (int)kid.size() < ABN_MAX_KERNELS);
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (timed) {
+                CUDA_TRY(cudaEventCreate(&e0));
+                CUDA_TRY(cudaEventCreate(&e1));
+                CUDA_TRY(cudaEventRecord(e0, ks));
             }
+            const int *list = d->dIdxSorted + hstart[b];
+            if (b == 0) {
+                n_unsupported = count;
+                unsupported_kernel<<<(count + 255) / 256, 256, 0, ks>>>(list, count, rp);
+            } else if (b == 1) {
+                gauss_kernel<<<(count + 127) / 128, 128, 0, ks>>>(d->m, c, d->dDescs, d->dChild, list, count, rp);
+            } else {
+                const int code = b - 2, icpt = code & 1, fk = code >> 1, fam = fk / (MAXK + 1), k = fk % (MAXK + 1);
+                FitLaunchFn fn = nullptr;
+                MnLaunchFn mfn = nullptr;
+                if (fam == 0) fn = (c.method == MLE) ? get_launch_bin_mle(k, icpt) : get_launch_bin_bayes(k, icpt);
+                else if (fam == 1) fn = get_launch_pois(k, icpt);
+                else mfn = get_launch_mn(fam, k, icpt);
+                if (mfn) {
+                    int grid = std::min((count + FIT_WARPS - 1) / FIT_WARPS, d->sm_count);
+                    mfn(d->m, c, d->dDescs, list, count, d->dCounters + b, rp, grid, ks);
+                } else if (!fn) {
+                    n_unsupported += count;
+                    unsupported_kernel<<<(count + 255) / 256, 256, 0, ks>>>(list, count, rp);
+                } else {
+                    int grid = std::min((count + FIT_WARPS - 1) / FIT_WARPS, d->sm_count * ABN_MIN_BLOCKS);
+                    fn(d->m, c, d->dDescs, d->dChild, list, count, d->dCounters + b, rp, grid, ks);
+                }
+            }
+            {
+                char what[64];
+                snprintf(what, sizeof(what), "fit kernel bucket %d (%d fits)", b, count);
+                KCHECK(what, ks);
+            }
+            if (timed) {
+                CUDA_TRY(cudaEventRecord(e1, ks));
+                kev0.push_back(e0);
+                kev1.push_back(e1);
+                kid.push_back(b);
+                kcount.push_back(count);
+                kstart.push_back(hstart[b]);
+            }
+            launches++;
         }
-        {
-            char what[64];
-            snprintf(what, sizeof(what), "fit kernel bucket %d (%d fits)", b, count);
-            KCHECK(what, s);
-        }
-        launches++;
     }
+    for (int i = 0; i < std::min(n_side, (int)abn_data::NSIDE); i++) {
+        cudaEvent_t done;
+        CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(done, d->side[i]));
+        CUDA_TRY(cudaStreamWaitEvent(s, done, 0));
+        cudaEventDestroy(done); // released once it has completed
+    }
+    cudaEventDestroy(planned);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev[3], s));
     std::vector<int> sorted_rows(rows);
@@ -573,7 +612,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     d->timing.n_kernels = (int)kid.size();
     for (size_t i = 0; i < kid.size(); i++) {
         float kms = 0;
-        cudaEventElapsedTime(&kms, kev[i], i + 1 < kid.size() ? kev[i + 1] : ev[3]);
+        cudaEventElapsedTime(&kms, kev0[i], kev1[i]);
         long long kb = 0;
         for (int t = 0; t < kcount[i]; t++) kb += fit_bytes(sorted_rows[kstart[i] + t]);
         d->timing.kernel_id[i] = kid[i];
@@ -581,7 +620,8 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
         d->timing.kernel_bytes[i] = kb;
         d->timing.kernel_ms[i] = kms;
     }
-    for (auto &e : kev) cudaEventDestroy(e);
+    for (auto &e : kev0) cudaEventDestroy(e);
+    for (auto &e : kev1) cudaEventDestroy(e);
     for (auto &e : ev) cudaEventDestroy(e);
     if (n_unsupported > 0 && n_unsupported == rows)
         return fail(err, errlen, ABN_ERR_LIMIT, "no candidate could be scored: designs wider than %d columns or multinomial children are not supported by this build", MAXK);

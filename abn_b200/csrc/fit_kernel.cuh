@@ -27,7 +27,18 @@ struct ResultPtrs {
     int *status, *iters;
 };
 
-constexpr int FIT_WARPS = 8; // warps per CTA
+// tunables (overridable at build time for sweeps: make EXTRA="-DABN_FIT_WARPS=.. -DABN_MIN_BLOCKS=.. -DABN_UNROLL=..")
+#ifndef ABN_FIT_WARPS
+#define ABN_FIT_WARPS 8
+#endif
+#ifndef ABN_MIN_BLOCKS
+#define ABN_MIN_BLOCKS 2
+#endif
+#ifndef ABN_UNROLL
+#define ABN_UNROLL 4
+#endif
+constexpr int FIT_WARPS = ABN_FIT_WARPS; // warps per CTA
+constexpr int FIT_UNROLL = ABN_UNROLL;   // rows per lane in flight
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -36,12 +47,48 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// contribution of one row to the register accumulators
+template <int KIND, int K, bool ICPT, bool NEED_H, bool NEED_G, bool NEED_L>
+__device__ __forceinline__ void row_update(const double (&xd)[K], double yi, const double (&beta)[K], const RowConst &rc,
+                                           double (&H)[K * (K + 1) / 2], double (&g)[K], double &ll, int &bad)
+{
+    // xd[j] holds design column j; with ICPT column 0 is the constant 1 and xd[0] is unused
+    double eta = ICPT ? beta[0] : 0.0;
+#pragma unroll
+    for (int j = (ICPT ? 1 : 0); j < K; j++) eta = fma(xd[j], beta[j], eta);
+    double w, r, l = 0.0;
+    RowOp<KIND>::template apply<NEED_H, NEED_G, NEED_L>(eta, yi, rc, w, r, l, bad);
+    if (NEED_H) {
+        int t = 0;
+#pragma unroll
+        for (int p = 0; p < K; p++) {
+            const double wx = (ICPT && p == 0) ? w : w * xd[p];
+#pragma unroll
+            for (int q = p; q < K; q++) {
+                H[t] = (ICPT && q == 0) ? (H[t] + wx) : fma(wx, xd[q], H[t]);
+                t++;
+            }
+        }
+    }
+    if (NEED_G) {
+#pragma unroll
+        for (int p = 0; p < K; p++) g[p] = (ICPT && p == 0) ? (g[p] + r) : fma(r, xd[p], g[p]);
+    }
+    if (NEED_L) ll += l;
+}
+
 // one pass of one fit by one warp. MODE is PASS_FULL / PASS_HG / PASS_GRAD / PASS_HESS / PASS_LL.
+// Lane l owns rows l, l+32, ...; FIT_UNROLL rows per lane form one iteration and the loads of the
+// next iteration are issued before the current one is computed (register double buffering), so the
+// L2 / HBM latency of the column reads is covered by a whole iteration of FP64 work. Rows are added
+// to the accumulators in increasing order, whatever FIT_UNROLL is.
 template <int KIND, int K, bool ICPT, int MODE>
 __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const double *const (&cp)[MAXK],
                                           const double *beta_sm, long long n, const RowConst rc, PassAcc *acc_sm)
 {
     constexpr int KD = K - (ICPT ? 1 : 0); // streamed design columns
+    constexpr int I0 = ICPT ? 1 : 0;
+    constexpr int U = FIT_UNROLL;
     constexpr bool NEED_H = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_HESS);
     constexpr bool NEED_G = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_GRAD);
     constexpr bool NEED_L = (MODE == PASS_FULL || MODE == PASS_LL);
@@ -60,35 +107,43 @@ __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const do
 #pragma unroll
     for (int j = 0; j < K; j++) g[j] = 0.0;
 
-#pragma unroll 2
-    for (long long i = lane; i < n; i += 32) {
-        double x[K];
-        if (ICPT) x[0] = 1.0;
+    const long long it_rows = 32LL * U;
+    const long long n_main = (n / it_rows) * it_rows;
+    double xn[U][K], yn[U]; // next iteration's rows
+    if (n_main > 0) {
 #pragma unroll
-        for (int j = 0; j < KD; j++) x[j + (ICPT ? 1 : 0)] = __ldg(cp[j] + i);
-        const double yi = __ldg(y + i);
-        double eta = ICPT ? beta[0] : 0.0;
+        for (int u = 0; u < U; u++) {
 #pragma unroll
-        for (int j = (ICPT ? 1 : 0); j < K; j++) eta = fma(x[j], beta[j], eta);
-        double w, r, l = 0.0;
-        RowOp<KIND>::template apply<NEED_H, NEED_G, NEED_L>(eta, yi, rc, w, r, l, bad);
-        if (NEED_H) {
-            int t = 0;
+            for (int j = 0; j < KD; j++) xn[u][j + I0] = __ldg(cp[j] + lane + 32 * u);
+            yn[u] = __ldg(y + lane + 32 * u);
+        }
+    }
+    for (long long base = lane; base < n_main; base += it_rows) {
+        double xc[U][K], yc[U];
 #pragma unroll
-            for (int p = 0; p < K; p++) {
-                const double wx = (ICPT && p == 0) ? w : w * x[p];
+        for (int u = 0; u < U; u++) {
 #pragma unroll
-                for (int q = p; q < K; q++) {
-                    H[t] = fma(wx, x[q], H[t]);
-                    t++;
-                }
+            for (int j = I0; j < K; j++) xc[u][j] = xn[u][j];
+            yc[u] = yn[u];
+        }
+        const long long nb = base + it_rows;
+        if (nb < n_main) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int j = 0; j < KD; j++) xn[u][j + I0] = __ldg(cp[j] + nb + 32 * u);
+                yn[u] = __ldg(y + nb + 32 * u);
             }
         }
-        if (NEED_G) {
 #pragma unroll
-            for (int p = 0; p < K; p++) g[p] = fma(r, x[p], g[p]);
-        }
-        if (NEED_L) ll += l;
+        for (int u = 0; u < U; u++)
+            row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L>(xc[u], yc[u], beta, rc, H, g, ll, bad);
+    }
+    for (long long i = n_main + lane; i < n; i += 32) { // tail: fewer than 32 * U rows
+        double xt[K];
+#pragma unroll
+        for (int j = 0; j < KD; j++) xt[j + I0] = __ldg(cp[j] + i);
+        row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L>(xt, __ldg(y + i), beta, rc, H, g, ll, bad);
     }
 
     // fixed-order butterfly: every lane ends with the same totals
@@ -116,20 +171,150 @@ __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const do
     }
 }
 
+
+#ifndef ABN_STAGE
+#define ABN_STAGE 1   // 1: stage the column tiles through shared memory with cp.async; 0: register double buffering
+#endif
+constexpr int FIT_STAGES = 2;
+
+// bytes of dynamic shared memory the staged pass needs per CTA
+template <int K, bool ICPT>
+constexpr size_t fit_stage_bytes()
+{
+    return ABN_STAGE ? (size_t)FIT_WARPS * FIT_STAGES * (K - (ICPT ? 1 : 0) + 1) * 32 * FIT_UNROLL * sizeof(double) : 0;
+}
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Staged variant of warp_pass: every lane copies the rows it owns (FIT_UNROLL rows x (KD+1)
+// columns per iteration) into its warp's shared-memory tile with cp.async, one iteration ahead,
+// and reads back only what it copied itself - so the only synchronisation is the lane's own
+// cp.async.wait_group, no registers are held by loads in flight, and the FP64 work of a whole
+// iteration covers the L2 / HBM latency. Same row order and reduction as the register variant.
+template <int KIND, int K, bool ICPT, int MODE>
+__device__ __forceinline__ void warp_pass_staged(const double *__restrict__ y, const double *const (&cp)[MAXK],
+                                                 const double *beta_sm, long long n, const RowConst rc,
+                                                 PassAcc *acc_sm, double *tile)
+{
+    constexpr int KD = K - (ICPT ? 1 : 0);
+    constexpr int I0 = ICPT ? 1 : 0;
+    constexpr int U = FIT_UNROLL;
+    constexpr int NC = KD + 1;          // staged columns: design columns + response
+    constexpr int TROWS = 32 * U;       // rows per iteration
+    constexpr bool NEED_H = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_HESS);
+    constexpr bool NEED_G = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_GRAD);
+    constexpr bool NEED_L = (MODE == PASS_FULL || MODE == PASS_LL);
+    const int lane = threadIdx.x & 31;
+
+    double beta[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) beta[j] = beta_sm[j];
+    double H[K * (K + 1) / 2];
+    double g[K];
+    double ll = 0.0;
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < K * (K + 1) / 2; j++) H[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; j++) g[j] = 0.0;
+
+    const long long n_main = (n / TROWS) * TROWS;
+    // tile layout: [stage][column][row in tile]; lane touches rows lane + 32 u only
+    auto issue = [&](long long base, int stage) {
+        double *t = tile + (size_t)stage * NC * TROWS;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int j = 0; j < KD; j++) cp_async8(t + j * TROWS + u * 32 + lane, cp[j] + base + u * 32 + lane);
+            cp_async8(t + KD * TROWS + u * 32 + lane, y + base + u * 32 + lane);
+        }
+        cp_async_commit();
+    };
+    if (n_main > 0) issue(0, 0);
+    int stage = 0;
+    for (long long base = 0; base < n_main; base += TROWS) {
+        const long long nb = base + TROWS;
+        if (nb < n_main) { issue(nb, stage ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        const double *t = tile + (size_t)stage * NC * TROWS;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            double xr[K];
+#pragma unroll
+            for (int j = 0; j < KD; j++) xr[j + I0] = t[j * TROWS + u * 32 + lane];
+            const double yi = t[KD * TROWS + u * 32 + lane];
+            row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L>(xr, yi, beta, rc, H, g, ll, bad);
+        }
+        stage ^= 1;
+    }
+    for (long long i = n_main + lane; i < n; i += 32) { // tail: fewer than 32 * U rows
+        double xt[K];
+#pragma unroll
+        for (int j = 0; j < KD; j++) xt[j + I0] = __ldg(cp[j] + i);
+        row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L>(xt, __ldg(y + i), beta, rc, H, g, ll, bad);
+    }
+
+    if (NEED_H) {
+#pragma unroll
+        for (int j = 0; j < K * (K + 1) / 2; j++) H[j] = warp_sum(H[j]);
+    }
+    if (NEED_G) {
+#pragma unroll
+        for (int j = 0; j < K; j++) g[j] = warp_sum(g[j]);
+    }
+    if (NEED_L) ll = warp_sum(ll);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        if (NEED_H) {
+#pragma unroll
+            for (int j = 0; j < K * (K + 1) / 2; j++) acc_sm->H[j] = H[j];
+        }
+        if (NEED_G) {
+#pragma unroll
+            for (int j = 0; j < K; j++) acc_sm->g[j] = g[j];
+        }
+        acc_sm->ll = ll;
+        acc_sm->bad = bad;
+    }
+}
+
+template <int KIND, int K, bool ICPT, int MODE>
+__device__ __forceinline__ void run_pass(const double *__restrict__ y, const double *const (&cp)[MAXK],
+                                         const double *beta_sm, long long n, const RowConst rc, PassAcc *acc_sm,
+                                         double *tile)
+{
+#if ABN_STAGE
+    warp_pass_staged<KIND, K, ICPT, MODE>(y, cp, beta_sm, n, rc, acc_sm, tile);
+#else
+    warp_pass<KIND, K, ICPT, MODE>(y, cp, beta_sm, n, rc, acc_sm);
+#endif
+}
+
 // KIND: RK_BIN_MLE, RK_BIN_BAYES or RK_POIS (both methods; the mle start-value pass uses RK_PINIT)
 template <int KIND, int K, bool ICPT>
-__global__ void __launch_bounds__(FIT_WARPS * 32, 2)
+__global__ void __launch_bounds__(FIT_WARPS * 32, ABN_MIN_BLOCKS)
 fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ child,
            const int *__restrict__ list, int count, int *counter, ResultPtrs out)
 {
     __shared__ FitState st_all[FIT_WARPS];
     __shared__ PassAcc acc_all[FIT_WARPS];
     __shared__ double exp_tab[32];
+    __shared__ double lnmu_tab[64];
+    extern __shared__ double stage_tiles[]; // FIT_WARPS x FIT_STAGES x (KD+1) x 32 FIT_UNROLL (staged pass)
     if (threadIdx.x < 32) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
+    if (KIND == RK_POIS && threadIdx.x < 64) lnmu_tab[threadIdx.x] = log((double)threadIdx.x + 0.1);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FitState &st = st_all[warp];
     PassAcc *acc = &acc_all[warp];
+    double *tile = stage_tiles + (size_t)warp * FIT_STAGES * (K - (ICPT ? 1 : 0) + 1) * 32 * FIT_UNROLL;
 
     for (;;) {
         int idx = 0;
@@ -148,7 +333,7 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
             cp[j] = m.X + (long long)(col < 0 ? 0 : col) * m.ld;
         }
         const double *y = m.X + (long long)d.ycol * m.ld;
-        const RowConst rc = make_row_const(K, (double)m.n, exp_tab);
+        const RowConst rc = make_row_const(K, (double)m.n, exp_tab, KIND == RK_POIS ? lnmu_tab : nullptr);
 
         int mode = 0;
         if (lane == 0) {
@@ -160,12 +345,12 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
         __syncwarp();
         while (mode != PASS_DONE) {
             // only the modes a row kind's state machines can ask for are instantiated
-            if (mode == PASS_HG) warp_pass<KIND, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc);
-            else if (mode == PASS_FULL) warp_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc);
-            else if (mode == PASS_LL) warp_pass<KIND, K, ICPT, PASS_LL>(y, cp, st.x, m.n, rc, acc);
-            else if (KIND != RK_BIN_MLE && mode == PASS_GRAD) warp_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc);
-            else if (KIND != RK_BIN_MLE && mode == PASS_HESS) warp_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc);
-            else if (KIND == RK_POIS && mode == PASS_PINIT) warp_pass<RK_PINIT, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc);
+            if (mode == PASS_HG) run_pass<KIND, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile);
+            else if (mode == PASS_FULL) run_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc, tile);
+            else if (mode == PASS_LL) run_pass<KIND, K, ICPT, PASS_LL>(y, cp, st.x, m.n, rc, acc, tile);
+            else if (KIND != RK_BIN_MLE && mode == PASS_GRAD) run_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc, tile);
+            else if (KIND != RK_BIN_MLE && mode == PASS_HESS) run_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc, tile);
+            else if (KIND == RK_POIS && mode == PASS_PINIT) run_pass<RK_PINIT, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile);
             __syncwarp();
             if (lane == 0) mode = fit_consume(st, c, *acc);
             mode = __shfl_sync(0xffffffffu, mode, 0);
@@ -193,7 +378,13 @@ template <int KIND, int K, bool ICPT>
 void launch_fit(const DataMeta &m, const Control &c, const FitDesc *descs, const int *child, const int *list,
                 int count, int *counter, ResultPtrs out, int grid, cudaStream_t stream)
 {
-    fit_kernel<KIND, K, ICPT><<<grid, FIT_WARPS * 32, 0, stream>>>(m, c, descs, child, list, count, counter, out);
+    constexpr size_t smem = fit_stage_bytes<K, ICPT>();
+    static bool configured = false; // one attribute call per instantiation and process
+    if (!configured && smem > 0) {
+        cudaFuncSetAttribute(fit_kernel<KIND, K, ICPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    fit_kernel<KIND, K, ICPT><<<grid, FIT_WARPS * 32, smem, stream>>>(m, c, descs, child, list, count, counter, out);
 }
 
 // defined in fit_bin_mle.cu / fit_bin_bayes.cu / fit_pois.cu: [k][icpt]

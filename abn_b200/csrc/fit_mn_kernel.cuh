@@ -1,0 +1,113 @@
+// fit_mn_kernel.cuh - streaming kernel for multinomial children (method = "mle"): one warp per
+// fit, same row partition and fixed-order reduction as fit_kernel.cuh. A pass evaluates the
+// softmax objective and its gradient at the current weights (solver_mn.cuh drives vmmin).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "fit_kernel.cuh"
+#include "rowops_mn.cuh"
+#include "solver_mn.cuh"
+
+namespace abn {
+
+template <int L, int K, bool ICPT>
+__device__ __forceinline__ void mn_warp_pass(const double *__restrict__ y0, long long ld, const double *const (&cp)[MAXK],
+                                             const double *w_sm, long long n, const double *tab, MnAcc *acc_sm)
+{
+    constexpr int KD = K - (ICPT ? 1 : 0);
+    constexpr int I0 = ICPT ? 1 : 0;
+    constexpr int NP = (L - 1) * K;
+    const int lane = threadIdx.x & 31;
+    double W[NP], g[NP], f = 0.0;
+#pragma unroll
+    for (int i = 0; i < NP; i++) { W[i] = w_sm[i]; g[i] = 0.0; }
+    int bad = 0;
+#pragma unroll 2
+    for (long long i = lane; i < n; i += 32) {
+        double x[K], yl[L - 1];
+        if (ICPT) x[0] = 1.0;
+#pragma unroll
+        for (int j = 0; j < KD; j++) x[j + I0] = __ldg(cp[j] + i);
+#pragma unroll
+        for (int l = 1; l < L; l++) yl[l - 1] = __ldg(y0 + (long long)l * ld + i);
+        mn_row<L, K, ICPT>(x, yl, W, tab, f, g);
+    }
+    f = warp_sum(f);
+#pragma unroll
+    for (int i = 0; i < NP; i++) g[i] = warp_sum(g[i]);
+    if (lane == 0) {
+        acc_sm->f = f;
+#pragma unroll
+        for (int i = 0; i < NP; i++) acc_sm->g[i] = g[i];
+        acc_sm->bad = bad;
+    }
+}
+
+template <int L, int K, bool ICPT>
+__global__ void __launch_bounds__(FIT_WARPS * 32, 1)
+fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ list,
+              int count, int *counter, ResultPtrs out)
+{
+    __shared__ MnState st_all[FIT_WARPS];
+    __shared__ MnAcc acc_all[FIT_WARPS];
+    __shared__ double exp_tab[32];
+    if (threadIdx.x < 32) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    MnState &st = st_all[warp];
+    MnAcc *acc = &acc_all[warp];
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(counter, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= count) break;
+        const int row = list[idx];
+        const FitDesc d = descs[row];
+        constexpr int KD = K - (ICPT ? 1 : 0);
+        const double *cp[MAXK];
+#pragma unroll
+        for (int j = 0; j < KD; j++) {
+            const int col = d.cols[j + (ICPT ? 1 : 0)];
+            cp[j] = m.X + (long long)(col < 0 ? 0 : col) * m.ld;
+        }
+        const double *y0 = m.X + (long long)d.ycol * m.ld;
+        int more = 0;
+        if (lane == 0) {
+            st.k = K; st.L = L; st.n = (double)m.n; st.rank = d.rank;
+            more = mn_begin(st) ? 1 : 0;
+        }
+        more = __shfl_sync(0xffffffffu, more, 0);
+        __syncwarp();
+        while (more) {
+            mn_warp_pass<L, K, ICPT>(y0, m.ld, cp, st.b, m.n, exp_tab, acc);
+            __syncwarp();
+            if (lane == 0) more = mn_consume(st, *acc) ? 1 : 0;
+            more = __shfl_sync(0xffffffffu, more, 0);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (out.mlik) out.mlik[row] = st.loglik;
+            if (out.aic) out.aic[row] = st.aic;
+            if (out.bic) out.bic[row] = st.bic;
+            if (out.mdl) out.mdl[row] = mdl_of(st.bic, d, c.nvars);
+            if (out.status) out.status[row] = st.status;
+            if (out.iters) out.iters[row] = st.passes;
+        }
+        __syncwarp();
+    }
+}
+
+typedef void (*MnLaunchFn)(const DataMeta &, const Control &, const FitDesc *, const int *, int, int *, ResultPtrs,
+                           int grid, cudaStream_t);
+
+template <int L, int K, bool ICPT>
+void launch_mn(const DataMeta &m, const Control &c, const FitDesc *descs, const int *list, int count, int *counter,
+               ResultPtrs out, int grid, cudaStream_t stream)
+{
+    fit_mn_kernel<L, K, ICPT><<<grid, FIT_WARPS * 32, 0, stream>>>(m, c, descs, list, count, counter, out);
+}
+
+MnLaunchFn get_launch_mn(int L, int k, int icpt); // fit_table.cu
+
+} // namespace abn

@@ -1,5 +1,6 @@
 // fit_table.cu - lookup of the streaming fit kernel launchers compiled from fit_inst.cu.
 #include "fit_kernel.cuh"
+#include "fit_mn_kernel.cuh"
 
 namespace abn {
 
@@ -29,5 +30,18 @@ static FitLaunchFn lookup(int kind, int k, int icpt)
 FitLaunchFn get_launch_bin_mle(int k, int icpt) { return lookup(RK_BIN_MLE, k, icpt); }
 FitLaunchFn get_launch_bin_bayes(int k, int icpt) { return lookup(RK_BIN_BAYES, k, icpt); }
 FitLaunchFn get_launch_pois(int k, int icpt) { return lookup(RK_POIS, k, icpt); }
+
+MnLaunchFn abn_mn_launch_1(int, int); MnLaunchFn abn_mn_launch_2(int, int); MnLaunchFn abn_mn_launch_3(int, int);
+MnLaunchFn abn_mn_launch_4(int, int); MnLaunchFn abn_mn_launch_5(int, int); MnLaunchFn abn_mn_launch_6(int, int);
+MnLaunchFn abn_mn_launch_7(int, int); MnLaunchFn abn_mn_launch_8(int, int);
+
+MnLaunchFn get_launch_mn(int L, int k, int icpt)
+{
+    typedef MnLaunchFn (*G)(int, int);
+    static const G g[MAXK + 1] = { nullptr, abn_mn_launch_1, abn_mn_launch_2, abn_mn_launch_3, abn_mn_launch_4,
+                                   abn_mn_launch_5, abn_mn_launch_6, abn_mn_launch_7, abn_mn_launch_8 };
+    if (k < 1 || k > MAXK || L < 2 || L > MN_MAXL) return nullptr;
+    return g[k](L, icpt);
+}
 
 } // namespace abn

@@ -39,20 +39,26 @@ struct FitDesc {
     short num_na;         // leading columns dropped (binomial, rank deficient)
     short family;         // child family
     short rank;           // rank of the full design as rank_cpp sees it
-    short err;            // 1 = design wider than MAXK
+    short err;            // 1 = design wider than MAXK, 2 = child not supported
+    short nlev;           // levels of a multinomial child (else 1)
+    short pad_;
 };
 
-// kernel bucket of a resolved fit: family-specific streaming kernels are instantiated per
-// (k, intercept); Gaussian fits go to the Gram-only kernel.
+// kernel bucket of a resolved fit: the streaming kernels are instantiated per (row kind, k,
+// intercept); Gaussian fits go to the Gram-only kernel. Family slots: 0 binomial, 1 Poisson,
+// 2.. multinomial child with 2, 3, ... levels.
+constexpr int MN_MAXL_ = 5;
+constexpr int NFAMSLOT = 2 + (MN_MAXL_ - 1);
 ABN_HD int bucket_of(const FitDesc &d)
 {
     if (d.err) return 0;
     if (d.family == GAUSSIAN) return 1;
     int icpt = (d.k > 0 && d.cols[0] < 0) ? 1 : 0;
-    int fam = d.family == BINOMIAL ? 0 : (d.family == POISSON ? 1 : 2);
+    int fam = d.family == BINOMIAL ? 0 : (d.family == POISSON ? 1 : d.nlev);
     return 2 + (fam * (MAXK + 1) + d.k) * 2 + icpt;
 }
-constexpr int NBUCKETS = 2 + 3 * (MAXK + 1) * 2;
+constexpr int NBUCKETS = 2 + NFAMSLOT * (MAXK + 1) * 2;
+static_assert(NBUCKETS <= 256, "bucket keys are bytes");
 
 ABN_HD int gidx(const FitDesc &d, int j) { return d.cols[j] < 0 ? 0 : 1 + d.cols[j]; }
 
@@ -93,6 +99,8 @@ ABN_HDN void resolve_design(const DataMeta &m, int method, int child, const int 
     d.ycol = m.node_col0[child];
     d.num_na = 0;
     d.err = 0;
+    d.nlev = (short)(m.node_col0[child + 1] - m.node_col0[child]);
+    d.pad_ = 0;
     bool any_multi = false;
     int kdata = 0;
     for (int j = 0; j < width; j++) {

@@ -23,16 +23,18 @@ enum RowKind : int {
 struct RowConst {
     double bp0, bp1;   // binomial MLE bias-reduced pseudo-responses for y = 0 / y = 1 (b' = bp0 + y (bp1 - bp0))
     const double *tab; // 2^(j/32) table for fast_exp (shared memory on the device)
+    const double *lnmu; // log(y + 0.1), y = 0..63, for the Poisson start values (may be null)
 };
 
 // b' = (y + 0.5 k/n) / (1 + k/n), irls_binomial_fast_br.cpp:58
-ABN_HD RowConst make_row_const(int k, double n, const double *tab)
+ABN_HD RowConst make_row_const(int k, double n, const double *tab, const double *lnmu = nullptr)
 {
     RowConst c;
     double dfn = (double)k / n;
     c.bp0 = (0.0 + dfn * 0.5) / (1 + dfn);
     c.bp1 = (1.0 + dfn * 0.5) / (1 + dfn);
     c.tab = tab;
+    c.lnmu = lnmu;
     return c;
 }
 
@@ -109,17 +111,20 @@ struct RowOp<RK_BIN_BAYES> {
 
 template <>
 struct RowOp<RK_PINIT> {
-    // mu = y + 0.1; eta0 = log(mu); W0 = exp(eta0); z0 = eta0 + (y - W0)/W0; H = X'W0X, g = X'W0z0
+    // mu = y + 0.1; eta0 = log(mu); W0 = exp(eta0) (= mu up to an ulp); z0 = eta0 + (y - W0)/W0;
+    // H = X'W0X, g = X'W0z0 with W0 z0 = W0 eta0 + (y - W0): no division needed. Counts are small
+    // integers, so log(y + 0.1) comes from a 64-entry table; other values take the libm path.
     template <bool NEED_W, bool NEED_R, bool NEED_L>
-    static ABN_HD void apply(double, double y, const RowConst &, double &w, double &r, double &l, int &bad)
+    static ABN_HD void apply(double, double y, const RowConst &c, double &w, double &r, double &l, int &bad)
     {
-        double mu = y + 0.1;
-        double eta0 = log(mu);
-        double W0 = exp(eta0);
-        double z0 = eta0 + (y - W0) / W0;
-        w = W0;
-        r = W0 * z0;
-        bad |= !isfinite(W0) | !isfinite(z0);
+        const double mu = y + 0.1;
+        const int yi = (int)y;
+        double eta0;
+        if (c.lnmu != nullptr && y == (double)yi && yi >= 0 && yi < 64) eta0 = c.lnmu[yi];
+        else eta0 = log(mu);
+        w = mu;
+        r = fma(mu, eta0, y - mu);
+        bad |= !(mu > 0.0) | !(mu < 1.79769313486231570815e308);
         if (NEED_L) l = 0.0;
     }
 };

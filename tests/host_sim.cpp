@@ -12,6 +12,8 @@
 #include "../abn_b200/csrc/plan.cuh"
 #include "../abn_b200/csrc/rowops.cuh"
 #include "../abn_b200/csrc/solver.cuh"
+#include "../abn_b200/csrc/rowops_mn.cuh"
+#include "../abn_b200/csrc/solver_mn.cuh"
 #include "../include/abn_b200.h"
 
 using namespace abn;
@@ -54,6 +56,56 @@ void run_pass(const DataMeta &m, const FitDesc &d, const Control &c, const FitSt
     if (d.family == POISSON) { host_pass<RK_POIS>(m, d, s.x, mode, a); return; }
     if (c.method == MLE) host_pass<RK_BIN_MLE>(m, d, s.x, mode, a);
     else host_pass<RK_BIN_BAYES>(m, d, s.x, mode, a);
+}
+
+// multinomial child: value + gradient pass, dispatched to the same mn_row<L, K, ICPT> the kernel uses
+template <int L, int K, bool ICPT>
+void mn_host_pass(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a)
+{
+    constexpr int NP = (L - 1) * K;
+    double W[NP], g[NP], f = 0.0;
+    for (int i = 0; i < NP; i++) { W[i] = w[i]; g[i] = 0.0; }
+    const double *y0 = m.X + (size_t)d.ycol * m.ld;
+    for (long long i = 0; i < m.n; i++) {
+        double x[K], yl[L - 1];
+        for (int j = 0; j < K; j++) x[j] = d.cols[j] < 0 ? 1.0 : m.X[(size_t)d.cols[j] * m.ld + i];
+        for (int l = 1; l < L; l++) yl[l - 1] = y0[(size_t)l * m.ld + i];
+        mn_row<L, K, ICPT>(x, yl, W, h_exp2_table, f, g);
+    }
+    a.f = f;
+    for (int i = 0; i < NP; i++) a.g[i] = g[i];
+    a.bad = 0;
+}
+
+template <int L, int K>
+void mn_pass_k(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a)
+{
+    if (d.cols[0] < 0) mn_host_pass<L, K, true>(m, d, w, a); else mn_host_pass<L, K, false>(m, d, w, a);
+}
+
+template <int L>
+void mn_pass_l(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a)
+{
+    switch (d.k) {
+    case 1: mn_pass_k<L, 1>(m, d, w, a); break;
+    case 2: mn_pass_k<L, 2>(m, d, w, a); break;
+    case 3: mn_pass_k<L, 3>(m, d, w, a); break;
+    case 4: mn_pass_k<L, 4>(m, d, w, a); break;
+    case 5: mn_pass_k<L, 5>(m, d, w, a); break;
+    case 6: mn_pass_k<L, 6>(m, d, w, a); break;
+    case 7: mn_pass_k<L, 7>(m, d, w, a); break;
+    case 8: mn_pass_k<L, 8>(m, d, w, a); break;
+    }
+}
+
+void mn_pass(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a)
+{
+    switch (d.nlev) {
+    case 2: mn_pass_l<2>(m, d, w, a); break;
+    case 3: mn_pass_l<3>(m, d, w, a); break;
+    case 4: mn_pass_l<4>(m, d, w, a); break;
+    case 5: mn_pass_l<5>(m, d, w, a); break;
+    }
 }
 
 } // namespace
@@ -99,8 +151,16 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
         if (buckets) buckets[r] = bucket_of(d);
         double ll = NAN, aic = NAN, bic = NAN, mdl = NAN;
         int status = FIT_NON_FINITE, passes = 0;
-        if (d.err || d.family == MULTINOMIAL || d.k == 0) {
+        if (d.err || d.k == 0 || (d.family == MULTINOMIAL && (d.nlev < 2 || d.nlev > MN_MAXL || c.method != MLE))) {
             // not supported by this build
+        } else if (d.family == MULTINOMIAL) {
+            MnState s;
+            std::memset(&s, 0, sizeof(s));
+            s.k = d.k; s.L = d.nlev; s.n = (double)m.n; s.rank = d.rank;
+            MnAcc a;
+            bool more = mn_begin(s);
+            while (more) { mn_pass(m, d, s.b, a); more = mn_consume(s, a); }
+            ll = s.loglik; aic = s.aic; bic = s.bic; status = s.status; passes = s.passes;
         } else if (c.method == MLE && d.family == GAUSSIAN) {
             gauss_mle_fit(m, d, &ll, &aic, &bic, &status);
             passes = 1;

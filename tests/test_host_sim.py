@@ -118,3 +118,29 @@ def test_synthetic_config4_small(method):
     ref = H.oracle_score(P, ch.astype(np.int32), par, ctrl)
     assert H.rel_err(sim["mlik"], ref["mlik"]).max() < 1e-9
     assert (sim["status"] == ref["status"]).all()
+
+
+def test_multinomial_child_vmmin_state_machine():
+    """R/build_score_cache_mle.R:319-331 (nnet + BFGS): the kernel's vmmin coroutine against the
+    oracle's straight port, on a 4-level child with ordinary and multinomial parents."""
+    names, data, dists, mp, _ = synth.make_config(5, n=4000, n_nodes=40)
+    keep = ["g1", "b1", "p1", "g2", "m1"]
+    data = {k: data[k] for k in keep}
+    dists = {k: dists[k] for k in keep}
+    P = prep.prepare(data, dists, "mle")
+    d = len(keep)
+    ch, nd = pyoracle.enumerate_mle(d, np.zeros((d, d), int), np.zeros((d, d), int), 3)
+    par = H.parents_from_node_defn(nd, 3)
+    ctrl = H.control("mle", d)
+    sim = H.sim_score(P, ch.astype(np.int32), par, ctrl)
+    ref = H.oracle_score(P, ch.astype(np.int32), par, ctrl)
+    m_child = ch == keep.index("m1")
+    assert m_child.sum() == 15
+    # same optimiser, same stopping rules; the row arithmetic differs in rounding only, and BFGS
+    # amplifies that to ~1e-9 of the objective at its (loose, reltol 1e-8) stopping point
+    for k in ("mlik", "aic", "bic", "mdl"):
+        assert H.rel_err(sim[k][m_child], ref[k][m_child]).max() < 1e-7, k
+    assert (sim["status"] == ref["status"]).all()
+    # children with the multinomial parent (4 one-hot columns, no intercept) stay at 1e-9
+    others = ~m_child
+    assert H.rel_err(sim["mlik"][others], ref["mlik"][others]).max() < 1e-9
