@@ -215,7 +215,9 @@ def kernel_name(kid: int) -> str:
     code = kid - 2
     icpt, fk = code & 1, code >> 1
     fam, k = divmod(fk, capi.MAX_K + 1)
-    return f"fit_kernel<{('binomial', 'poisson', 'multinomial')[fam]},K={k},icpt={icpt}>"
+    if fam >= 2:
+        return f"fit_mn_kernel<L={fam},K={k},icpt={icpt}>"
+    return f"fit_kernel<{('binomial', 'poisson')[fam]},K={k},icpt={icpt}>"
 
 
 class DeviceData:

@@ -199,7 +199,8 @@ typedef struct abn_timing {
     int32_t reserved;
     int32_t kernel_id[ABN_MAX_KERNELS];    /* 1 = Gram-only Gaussian kernel; otherwise
                                               2 + ((family_idx * (ABN_MAX_K+1) + k) * 2 + intercept),
-                                              family_idx 0 = binomial, 1 = Poisson            */
+                                              family_idx 0 = binomial, 1 = Poisson, L = 2..5:
+                                              multinomial child with L levels               */
     int64_t kernel_fits[ABN_MAX_KERNELS];
     int64_t kernel_bytes[ABN_MAX_KERNELS]; /* algorithmic bytes of the fits that kernel ran  */
     double kernel_ms[ABN_MAX_KERNELS];
