@@ -119,4 +119,35 @@ ABN_HD double fast_rcp_approx(double d)
 #endif
 }
 
+// log(x) for finite x >= 1 (every use in the row ops: 1 + e, 1 + E, a softmax denominator).
+//   x = 2^e m, m in [1,2), i = top 6 mantissa bits, c_i = 1/(1 + i/64), r = m c_i - 1 in [0, 1/64)
+//   log x = e ln2 + log(1 + i/64) + log1p(r)
+// `tab` holds {c_i, log(1 + i/64)} pairs (64 x 2 doubles; shared memory on the device). Absolute
+// error < 3e-16, relative error ~1 ulp away from x = 1 and exact-ish near it (c_0 = 1, r = m - 1).
+ABN_HD void fill_log_table(double *tab, int i)
+{
+    const double mi = 1.0 + (double)i / 64.0;
+    tab[2 * i] = 1.0 / mi;
+    tab[2 * i + 1] = log(mi);
+}
+
+ABN_HD double fast_log_ge1(double x, const double *tab)
+{
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const uint64_t b = double_to_bits(x);
+    const int e = (int)(b >> 52) - 1023;
+    const int i = (int)((b >> 46) & 63);
+    const double m = bits_to_double((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+    const double r = fma(m, tab[2 * i], -1.0);
+    double p = fma(r, -1.0 / 8.0, 1.0 / 7.0);
+    p = fma(p, r, -1.0 / 6.0);
+    p = fma(p, r, 1.0 / 5.0);
+    p = fma(p, r, -1.0 / 4.0);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    p = fma(p * r, r, r);                       // log1p(r)
+    const double ed = (double)e;
+    return fma(ed, LN2_HI, tab[2 * i + 1] + fma(ed, LN2_LO, p));
+}
+
 } // namespace abn

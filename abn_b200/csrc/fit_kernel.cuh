@@ -307,6 +307,8 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
     __shared__ PassAcc acc_all[FIT_WARPS];
     __shared__ double exp_tab[32];
     __shared__ double lnmu_tab[64];
+    __shared__ double log_tab[128];
+    if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
     extern __shared__ double stage_tiles[]; // FIT_WARPS x FIT_STAGES x (KD+1) x 32 FIT_UNROLL (staged pass)
     if (threadIdx.x < 32) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
     if (KIND == RK_POIS && threadIdx.x < 64) lnmu_tab[threadIdx.x] = log((double)threadIdx.x + 0.1);
@@ -333,7 +335,7 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
             cp[j] = m.X + (long long)(col < 0 ? 0 : col) * m.ld;
         }
         const double *y = m.X + (long long)d.ycol * m.ld;
-        const RowConst rc = make_row_const(K, (double)m.n, exp_tab, KIND == RK_POIS ? lnmu_tab : nullptr);
+        const RowConst rc = make_row_const(K, (double)m.n, exp_tab, log_tab, KIND == RK_POIS ? lnmu_tab : nullptr);
 
         int mode = 0;
         if (lane == 0) {

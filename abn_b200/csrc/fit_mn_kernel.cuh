@@ -13,7 +13,7 @@ namespace abn {
 
 template <int L, int K, bool ICPT>
 __device__ __forceinline__ void mn_warp_pass(const double *__restrict__ y0, long long ld, const double *const (&cp)[MAXK],
-                                             const double *w_sm, long long n, const double *tab, MnAcc *acc_sm)
+                                             const double *w_sm, long long n, const double *tab, const double *logtab, MnAcc *acc_sm)
 {
     constexpr int KD = K - (ICPT ? 1 : 0);
     constexpr int I0 = ICPT ? 1 : 0;
@@ -31,7 +31,7 @@ __device__ __forceinline__ void mn_warp_pass(const double *__restrict__ y0, long
         for (int j = 0; j < KD; j++) x[j + I0] = __ldg(cp[j] + i);
 #pragma unroll
         for (int l = 1; l < L; l++) yl[l - 1] = __ldg(y0 + (long long)l * ld + i);
-        mn_row<L, K, ICPT>(x, yl, W, tab, f, g);
+        mn_row<L, K, ICPT>(x, yl, W, tab, logtab, f, g);
     }
     f = warp_sum(f);
 #pragma unroll
@@ -52,7 +52,9 @@ fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ des
     __shared__ MnState st_all[FIT_WARPS];
     __shared__ MnAcc acc_all[FIT_WARPS];
     __shared__ double exp_tab[32];
+    __shared__ double log_tab[128];
     if (threadIdx.x < 32) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
+    if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     MnState &st = st_all[warp];
@@ -80,7 +82,7 @@ fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ des
         more = __shfl_sync(0xffffffffu, more, 0);
         __syncwarp();
         while (more) {
-            mn_warp_pass<L, K, ICPT>(y0, m.ld, cp, st.b, m.n, exp_tab, acc);
+            mn_warp_pass<L, K, ICPT>(y0, m.ld, cp, st.b, m.n, exp_tab, log_tab, acc);
             __syncwarp();
             if (lane == 0) more = mn_consume(st, *acc) ? 1 : 0;
             more = __shfl_sync(0xffffffffu, more, 0);

@@ -24,10 +24,11 @@ struct RowConst {
     double bp0, bp1;   // binomial MLE bias-reduced pseudo-responses for y = 0 / y = 1 (b' = bp0 + y (bp1 - bp0))
     const double *tab; // 2^(j/32) table for fast_exp (shared memory on the device)
     const double *lnmu; // log(y + 0.1), y = 0..63, for the Poisson start values (may be null)
+    const double *logtab; // fast_log_ge1 table
 };
 
 // b' = (y + 0.5 k/n) / (1 + k/n), irls_binomial_fast_br.cpp:58
-ABN_HD RowConst make_row_const(int k, double n, const double *tab, const double *lnmu = nullptr)
+ABN_HD RowConst make_row_const(int k, double n, const double *tab, const double *logtab, const double *lnmu = nullptr)
 {
     RowConst c;
     double dfn = (double)k / n;
@@ -35,6 +36,7 @@ ABN_HD RowConst make_row_const(int k, double n, const double *tab, const double 
     c.bp1 = (1.0 + dfn * 0.5) / (1 + dfn);
     c.tab = tab;
     c.lnmu = lnmu;
+    c.logtab = logtab;
     return c;
 }
 
@@ -71,7 +73,7 @@ struct RowOp<RK_BIN_MLE> {
             w = rho * gp;
             r = rho * (fma(y, c.bp1 - c.bp0, c.bp0) - g);
         }
-        if (NEED_L) l = -log(d) - (1.0 - y) * eta;
+        if (NEED_L) l = -fast_log_ge1(d, c.logtab) - (1.0 - y) * eta;
     }
 };
 
@@ -104,7 +106,7 @@ struct RowOp<RK_BIN_BAYES> {
             w = sig * inv;
             r = y - sig;
         }
-        if (NEED_L) l = (eta > 700.0) ? (y * eta - eta) : (y * eta - log(d));
+        if (NEED_L) l = (eta > 700.0) ? (y * eta - eta) : (y * eta - fast_log_ge1(d, c.logtab));
         (void)bad;
     }
 };

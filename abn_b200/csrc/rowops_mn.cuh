@@ -10,7 +10,7 @@ namespace abn {
 // indicator of level l (l = 1..L-1; level 0 is the reference), W: (L-1) x K weights.
 template <int L, int K, bool ICPT>
 ABN_HD void mn_row(const double (&x)[K], const double (&yl)[L - 1], const double (&W)[(L - 1) * K],
-                   const double *tab, double &f, double (&g)[(L - 1) * K])
+                   const double *tab, const double *logtab, double &f, double (&g)[(L - 1) * K])
 {
     double o[L];
     o[0] = 0.0;
@@ -31,7 +31,7 @@ ABN_HD void mn_row(const double (&x)[K], const double (&yl)[L - 1], const double
     double oy = 0.0; // o of the observed level
 #pragma unroll
     for (int l = 1; l < L; l++) oy = fma(yl[l - 1], o[l], oy);
-    f -= (oy - mx) - log(sum); // - log p_y
+    f -= (oy - mx) - fast_log_ge1(sum, logtab); // - log p_y (sum >= 1: the largest term is exp(0))
 #pragma unroll
     for (int l = 1; l < L; l++) {
         const double e = fma(p[l], inv, -yl[l - 1]);

@@ -92,6 +92,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Host cores the CPU arm may use (torchrun exports OMP_NUM_THREADS=1, which would starve it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def make_data(n, n_nodes):
     from abn_b200 import prep, synth
     names, data, dists, mp, _ = synth.make_config(CFG, n=n, n_nodes=n_nodes)
@@ -147,7 +155,7 @@ def main():
     # ------------------------------------------------------------------------------------------------
     if args.impl == "reference":
         from oracle import pyoracle
-        threads = pyoracle.num_threads()
+        threads = host_threads()
         sample = max(threads, min(args.cpu_sample, args.batch))
         times = []
         for step in range(args.warmup + args.steps):
@@ -300,7 +308,7 @@ def main():
     cpu = None
     try:
         from oracle import pyoracle
-        threads = pyoracle.num_threads()
+        threads = host_threads()
         rows = batch_rows(total_rows, args.batch, args.block, args.warmup, 0, world)
         sample = max(threads, min(args.cpu_sample, len(rows)))
         rows = rows[:: max(1, len(rows) // sample)][:sample]

@@ -20,12 +20,20 @@ using namespace abn;
 
 namespace {
 
+const double *host_log_table()
+{
+    static double tab[128];
+    static bool done = false;
+    if (!done) { for (int i = 0; i < 64; i++) fill_log_table(tab, i); done = true; }
+    return tab;
+}
+
 template <int KIND>
 void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode, PassAcc &a)
 {
     const int k = d.k;
     std::memset(&a, 0, sizeof(a));
-    RowConst rc = make_row_const(k, (double)m.n, h_exp2_table);
+    RowConst rc = make_row_const(k, (double)m.n, h_exp2_table, host_log_table());
     const double *y = m.X + (size_t)d.ycol * m.ld;
     const bool need_h = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_HESS);
     const bool need_g = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_GRAD);
@@ -70,7 +78,7 @@ void mn_host_pass(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a
         double x[K], yl[L - 1];
         for (int j = 0; j < K; j++) x[j] = d.cols[j] < 0 ? 1.0 : m.X[(size_t)d.cols[j] * m.ld + i];
         for (int l = 1; l < L; l++) yl[l - 1] = y0[(size_t)l * m.ld + i];
-        mn_row<L, K, ICPT>(x, yl, W, h_exp2_table, f, g);
+        mn_row<L, K, ICPT>(x, yl, W, h_exp2_table, host_log_table(), f, g);
     }
     a.f = f;
     for (int i = 0; i < NP; i++) a.g[i] = g[i];
@@ -113,6 +121,7 @@ void mn_pass(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a)
 extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand, const abn_control *ctrl,
                                abn_result *out, int *buckets /* optional [rows] */)
 {
+    host_log_table(); // initialise before the parallel region
     const long long n = ds->n;
     const int D = 1 + ds->n_cols + ds->n_nodes;
     // Z = [1 | X | log(y + 0.1) of Poisson nodes], G = Z'Z
@@ -191,6 +200,11 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
 }
 
 // fast FP64 math of the kernels (fastmath.cuh), host build, for tests/test_fastmath.py
+extern "C" void sim_fast_log(const double *x, double *out, long n)
+{
+    for (long i = 0; i < n; i++) out[i] = fast_log_ge1(x[i], host_log_table());
+}
+
 extern "C" void sim_fast_exp(const double *t, double *out, long n)
 {
     for (long i = 0; i < n; i++) out[i] = fast_exp(t[i], h_exp2_table);

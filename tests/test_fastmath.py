@@ -31,3 +31,20 @@ def test_fast_exp_about_one_ulp_over_the_working_range():
 def test_fast_exp_exact_points():
     got = _fast_exp(np.array([0.0, math.log(2.0) * 0]))
     assert got[0] == 1.0
+
+
+def test_fast_log_for_arguments_at_least_one():
+    lib = H.sim_lib()
+    lib.sim_fast_log.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_long]
+    rng = np.random.default_rng(1)
+    x = np.concatenate([1.0 + np.exp(rng.uniform(-40, 40, 300_000)), rng.uniform(1, 6, 200_000),
+                        np.array([1.0, 1.0 + 2 ** -52, 2.0, 4.0, 1e300, 1.0 + 1e-10])])
+    out = np.empty_like(x)
+    lib.sim_fast_log(x.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)), len(x))
+    ref = np.log(x.astype(np.longdouble))
+    abs_err = np.abs(out.astype(np.longdouble) - ref).astype(np.float64)
+    rel_err = abs_err / np.maximum(np.abs(ref.astype(np.float64)), 1e-300)
+    # sums of log terms need absolute accuracy near x = 1 and ~ulp relative accuracy elsewhere
+    assert (abs_err / np.maximum(1.0, np.abs(ref.astype(np.float64)))).max() < 4e-16
+    assert rel_err[x > 1.5].max() < 5e-16
+    assert out[-6] == 0.0 and abs_err[-1] < 1e-25  # near 1: r = m - 1 exactly, log1p series
