@@ -74,9 +74,13 @@ __device__ __forceinline__ double z_value(const DataMeta &m, int a, long long i)
 {
     if (a == 0) return 1.0;
     if (a <= m.n_cols) return __ldg(m.X + (long long)(a - 1) * m.ld + i);
-    const int node = a - 1 - m.n_cols;
+    int node = a - 1 - m.n_cols;
+    const bool wz0 = node >= m.n_nodes; // second block of virtual columns: W0 z0 of the Poisson mle start
+    if (wz0) node -= m.n_nodes;
     if (m.node_family[node] != POISSON) return 0.0;
-    return log(__ldg(m.X + (long long)m.node_col0[node] * m.ld + i) + 0.1);
+    const double y = __ldg(m.X + (long long)m.node_col0[node] * m.ld + i);
+    const double mu = y + 0.1, eta0 = log(mu);
+    return wz0 ? fma(mu, eta0, y - mu) : eta0;
 }
 
 // grid.x = row chunks, grid.y = groups of GRAM_THREADS tile pairs. Each thread owns one GT x GT
@@ -84,9 +88,12 @@ __device__ __forceinline__ double z_value(const DataMeta &m, int a, long long i)
 // memory (row-major, padded) and every thread sweeps them. Partial tiles go to
 // part[chunk][pair][GT*GT]; gram_reduce sums the chunks in a fixed order.
 __global__ void __launch_bounds__(GRAM_THREADS)
-gram_partial(const DataMeta m, int T, int NP, int RC, int Dp, long long rows_per_chunk, double *__restrict__ part)
+gram_partial(const DataMeta m, int Dz, int wnode, int T, int NP, int RC, int Dp, long long rows_per_chunk,
+             double *__restrict__ part)
 {
-    extern __shared__ double zs[]; // RC x Dp
+    // Dz: columns of Z used (m.D for the global Gram, m.D0 for a weighted one); wnode >= 0: weight
+    // rows by (y_wnode + 0.1) (the Poisson mle start weights of child wnode)
+    extern __shared__ double zs[]; // RC x Dp, then RC weights
     const int pair = blockIdx.y * GRAM_THREADS + threadIdx.x;
     int I = 0, J = 0;
     if (pair < NP) { // unrank (I, J), I <= J, row-major over the upper triangle
@@ -106,21 +113,25 @@ gram_partial(const DataMeta m, int T, int NP, int RC, int Dp, long long rows_per
         const int nr = (int)min((long long)RC, r1 - base);
         __syncthreads();
         // coalesced along rows within a column; transposed store
-        for (int e = threadIdx.x; e < RC * m.D; e += GRAM_THREADS) {
+        double *ws = zs + (size_t)RC * Dp;
+        for (int e = threadIdx.x; e < RC * Dz; e += GRAM_THREADS) {
             const int col = e / RC, r = e - col * RC;
             zs[r * Dp + col] = (r < nr) ? z_value(m, col, base + r) : 0.0;
         }
         // zero the padding columns the last tile may touch
-        for (int e = threadIdx.x; e < RC * (Dp - m.D); e += GRAM_THREADS) {
-            const int r = e / (Dp - m.D), col = m.D + (e - r * (Dp - m.D));
+        for (int e = threadIdx.x; e < RC * (Dp - Dz); e += GRAM_THREADS) {
+            const int r = e / (Dp - Dz), col = Dz + (e - r * (Dp - Dz));
             zs[r * Dp + col] = 0.0;
         }
+        for (int r = threadIdx.x; r < RC; r += GRAM_THREADS)
+            ws[r] = (wnode >= 0 && r < nr) ? __ldg(m.X + (long long)m.node_col0[wnode] * m.ld + base + r) + 0.1 : 1.0;
         __syncthreads();
         if (pair < NP) {
             for (int r = 0; r < nr; r++) {
                 double a[GT], b[GT];
+                const double wr = ws[r];
 #pragma unroll
-                for (int t = 0; t < GT; t++) { a[t] = zs[r * Dp + I * GT + t]; b[t] = zs[r * Dp + J * GT + t]; }
+                for (int t = 0; t < GT; t++) { a[t] = zs[r * Dp + I * GT + t] * wr; b[t] = zs[r * Dp + J * GT + t]; }
 #pragma unroll
                 for (int s = 0; s < GT; s++)
 #pragma unroll
@@ -253,9 +264,10 @@ gauss_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ desc
 struct abn_data {
     int device = 0;
     DataMeta m{};
-    double *dX = nullptr, *dG = nullptr, *dLfact = nullptr;
-    int *dFamily = nullptr, *dCol0 = nullptr;
-    std::vector<int> family, col0;
+    double *dX = nullptr, *dG = nullptr, *dLfact = nullptr, *dGw = nullptr;
+    int *dFamily = nullptr, *dCol0 = nullptr, *dGwIndex = nullptr;
+    std::vector<int> family, col0, gw_index;
+    bool gw_ready = false;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     static constexpr int NSIDE = 3;
@@ -289,23 +301,25 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
     cudaSetDevice(d->device);
     free_scratch(d);
     cudaFree(d->dX); cudaFree(d->dG); cudaFree(d->dLfact); cudaFree(d->dFamily); cudaFree(d->dCol0);
+    cudaFree(d->dGw); cudaFree(d->dGwIndex);
     cudaFree(d->dBucketStart); cudaFree(d->dCounters);
     if (d->stream) cudaStreamDestroy(d->stream);
     for (auto &ss : d->side) if (ss) cudaStreamDestroy(ss);
     delete d;
 }
 
-static int compute_gram(abn_data *d, char *err, size_t errlen)
+// one Gram matrix: Dz columns of Z, optional row weights (y_wnode + 0.1), result Dz x Dz at dst
+static int launch_gram(abn_data *d, int Dz, int wnode, double *dst, double **part_io, size_t *part_cap,
+                       char *err, size_t errlen)
 {
     const DataMeta &m = d->m;
-    const int D = m.D;
-    const int T = (D + GT - 1) / GT;
+    const int T = (Dz + GT - 1) / GT;
     const int NP = T * (T + 1) / 2;
     const int Dp = T * GT + 1; // padded smem row, odd-ish stride
     int RC = 64;
-    while (RC > 8 && (size_t)RC * Dp * sizeof(double) > 160 * 1024) RC >>= 1;
-    if ((size_t)RC * Dp * sizeof(double) > 200 * 1024)
-        return fail(err, errlen, ABN_ERR_LIMIT, "data set has too many columns for the Gram kernel (D=%d)", D);
+    while (RC > 8 && (size_t)RC * (Dp + 1) * sizeof(double) > 160 * 1024) RC >>= 1;
+    if ((size_t)RC * (Dp + 1) * sizeof(double) > 200 * 1024)
+        return fail(err, errlen, ABN_ERR_LIMIT, "data set has too many columns for the Gram kernel (D=%d)", Dz);
     const int gy = (NP + GRAM_THREADS - 1) / GRAM_THREADS;
     int chunks = std::max(1, (2 * d->sm_count) / gy);
     long long rpc = (m.n + chunks - 1) / chunks;
@@ -313,19 +327,59 @@ static int compute_gram(abn_data *d, char *err, size_t errlen)
     if (rpc < RC) rpc = RC;
     chunks = (int)((m.n + rpc - 1) / rpc);
     if (chunks < 1) chunks = 1;
+    const size_t need = (size_t)chunks * NP * GT * GT * sizeof(double);
+    if (need > *part_cap) {
+        cudaStreamSynchronize(d->stream);
+        cudaFree(*part_io);
+        *part_io = nullptr;
+        CUDA_TRY(cudaMalloc(part_io, need));
+        *part_cap = need;
+    }
+    const size_t smem = (size_t)RC * (Dp + 1) * sizeof(double);
+    CUDA_TRY(cudaFuncSetAttribute(gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    gram_partial<<<dim3(chunks, gy), GRAM_THREADS, smem, d->stream>>>(m, Dz, wnode, T, NP, RC, Dp, rpc, *part_io);
+    gram_reduce<<<(NP * GT * GT + 255) / 256, 256, 0, d->stream>>>(Dz, T, NP, chunks, *part_io, dst);
+    d->timing.launches += 2;
+    return ABN_OK;
+}
+
+static int compute_gram(abn_data *d, char *err, size_t errlen)
+{
+    const DataMeta &m = d->m;
     double *part = nullptr;
-    CUDA_TRY(cudaMalloc(&part, (size_t)chunks * NP * GT * GT * sizeof(double)));
-    const size_t smem = (size_t)RC * Dp * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { cudaFree(part); CUDA_TRY(e); }
-    gram_partial<<<dim3(chunks, gy), GRAM_THREADS, smem, d->stream>>>(m, T, NP, RC, Dp, rpc, part);
-    gram_reduce<<<(NP * GT * GT + 255) / 256, 256, 0, d->stream>>>(D, T, NP, chunks, part, d->dG);
-    lfact_kernel<<<m.n_nodes, 256, 0, d->stream>>>(m, d->dLfact);
-    e = cudaStreamSynchronize(d->stream);
+    size_t part_cap = 0;
+    int rc = launch_gram(d, m.D, -1, d->dG, &part, &part_cap, err, errlen);
+    if (rc == ABN_OK) {
+        lfact_kernel<<<m.n_nodes, 256, 0, d->stream>>>(m, d->dLfact);
+        d->timing.launches += 1;
+    }
+    cudaError_t e = cudaStreamSynchronize(d->stream);
     cudaFree(part);
+    if (rc != ABN_OK) return rc;
     CUDA_TRY(e);
     CUDA_TRY(cudaGetLastError());
-    d->timing.launches += 3;
+    return ABN_OK;
+}
+
+// weighted Gram matrices of the Poisson children (start values of the mle without a data pass);
+// computed on the first mle call on a data set, never for bayes
+static int ensure_weighted_grams(abn_data *d, char *err, size_t errlen)
+{
+    if (d->gw_ready) return ABN_OK;
+    const DataMeta &m = d->m;
+    double *part = nullptr;
+    size_t part_cap = 0;
+    int rc = ABN_OK;
+    for (int v = 0; rc == ABN_OK && v < m.n_nodes; v++) {
+        if (d->family[v] != ABN_POISSON) continue;
+        rc = launch_gram(d, m.D0, v, d->dGw + (size_t)d->gw_index[v] * m.D0 * m.D0, &part, &part_cap, err, errlen);
+    }
+    cudaError_t e = cudaStreamSynchronize(d->stream);
+    cudaFree(part);
+    if (rc != ABN_OK) return rc;
+    CUDA_TRY(e);
+    CUDA_TRY(cudaGetLastError());
+    d->gw_ready = true;
     return ABN_OK;
 }
 
@@ -362,7 +416,11 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     d->col0.assign(ds->node_col0, ds->node_col0 + ds->n_nodes + 1);
 
     const long long ld = ((ds->n + 15) / 16) * 16; // 128-byte aligned columns
-    const int D = 1 + ds->n_cols + ds->n_nodes;
+    const int D = 1 + ds->n_cols + 2 * ds->n_nodes;
+    const int D0 = 1 + ds->n_cols;
+    int n_pois = 0;
+    d->gw_index.assign(ds->n_nodes, -1);
+    for (int i = 0; i < ds->n_nodes; i++) if (ds->node_family[i] == ABN_POISSON) d->gw_index[i] = n_pois++;
     int rc = ABN_OK;
 #define TRY_OR_FREE(expr)                                                       \
     do {                                                                        \
@@ -382,6 +440,8 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     TRY_OR_FREE(cudaMalloc(&d->dLfact, (size_t)ds->n_nodes * sizeof(double)));
     TRY_OR_FREE(cudaMalloc(&d->dFamily, (size_t)ds->n_nodes * sizeof(int)));
     TRY_OR_FREE(cudaMalloc(&d->dCol0, (size_t)(ds->n_nodes + 1) * sizeof(int)));
+    TRY_OR_FREE(cudaMalloc(&d->dGwIndex, (size_t)ds->n_nodes * sizeof(int)));
+    TRY_OR_FREE(cudaMalloc(&d->dGw, std::max<size_t>(1, (size_t)n_pois * D0 * D0) * sizeof(double)));
     TRY_OR_FREE(cudaMalloc(&d->dBucketStart, (size_t)(NBUCKETS + 1) * sizeof(int)));
     TRY_OR_FREE(cudaMalloc(&d->dCounters, (size_t)(NBUCKETS + 1) * sizeof(int)));
     TRY_OR_FREE(cudaMemsetAsync(d->dX, 0, (size_t)ld * ds->n_cols * sizeof(double), d->stream));
@@ -389,6 +449,7 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
                                   (size_t)ds->n * sizeof(double), (size_t)ds->n_cols, cudaMemcpyHostToDevice, d->stream));
     TRY_OR_FREE(cudaMemcpyAsync(d->dFamily, ds->node_family, (size_t)ds->n_nodes * sizeof(int), cudaMemcpyHostToDevice, d->stream));
     TRY_OR_FREE(cudaMemcpyAsync(d->dCol0, ds->node_col0, (size_t)(ds->n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    TRY_OR_FREE(cudaMemcpyAsync(d->dGwIndex, d->gw_index.data(), (size_t)ds->n_nodes * sizeof(int), cudaMemcpyHostToDevice, d->stream));
     TRY_OR_FREE(cudaStreamSynchronize(d->stream));
 #undef TRY_OR_FREE
     d->m.n = ds->n;
@@ -401,6 +462,9 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     d->m.node_family = d->dFamily;
     d->m.node_col0 = d->dCol0;
     d->m.node_lfact = d->dLfact;
+    d->m.Gw = d->dGw;
+    d->m.node_gw = d->dGwIndex;
+    d->m.D0 = D0;
     rc = compute_gram(d, err, errlen);
     if (rc != ABN_OK) { abn_b200_data_destroy(d); return rc; }
     *out = d;
@@ -459,6 +523,10 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     CUDA_TRY(cudaSetDevice(d->device));
     int rc = ensure_scratch(d, rows, width, err, errlen);
     if (rc != ABN_OK) return rc;
+    if (ctrl->method == ABN_METHOD_MLE) {
+        rc = ensure_weighted_grams(d, err, errlen);
+        if (rc != ABN_OK) return rc;
+    }
 
     cudaEvent_t ev[5];
     for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));

@@ -342,6 +342,17 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
             state_setup(m, d, ch, c, st);
             if (c.method == BAYES) bayes_inits(m, d, ch, st);
             mode = fit_begin(st, c);
+            if (KIND == RK_BIN_MLE) { // iteration 1 from the Gram matrix, no data pass
+                binomial_first_acc(m, d, *acc);
+                st.have_ll = 1;
+                mode = fit_consume(st, c, *acc);
+                st.passes--;
+            }
+            if (KIND == RK_POIS && mode == PASS_PINIT) { // start values from the child's weighted Gram
+                poisson_init_acc(m, d, ch, *acc);
+                mode = fit_consume(st, c, *acc);
+                st.passes--;
+            }
         }
         mode = __shfl_sync(0xffffffffu, mode, 0);
         __syncwarp();

@@ -18,17 +18,22 @@ struct DataMeta {
     long long n;     // observations
     long long ld;    // leading dimension (elements) of the column-major matrix
     int n_nodes, n_cols;
-    int D;           // Gram dimension = 1 + n_cols + n_nodes
+    int D;           // Gram dimension = 1 + n_cols + 2 n_nodes
     const double *X; // column-major, ld x n_cols
     const double *G; // D x D row-major symmetric
     const int *node_family; // [n_nodes]
     const int *node_col0;   // [n_nodes + 1]
     const double *node_lfact; // [n_nodes] sum lgamma(y + 1) (Poisson nodes, else 0)
+    const double *Gw;         // per Poisson node: Z0' diag(y + 0.1) Z0, Z0 = [1 | X], D0 x D0 each
+    const int *node_gw;       // [n_nodes] ordinal of the node's block in Gw, -1 if not Poisson
+    int D0;                   // 1 + n_cols
 };
 
 ABN_HD int gram_icpt() { return 0; }
 ABN_HD int gram_col(int c) { return 1 + c; }
 ABN_HD int gram_logy(const DataMeta &m, int node) { return 1 + m.n_cols + node; }
+// virtual column W0 z0 = (y + 0.1) log(y + 0.1) + (y - (y + 0.1)) of a Poisson node (start values of the mle)
+ABN_HD int gram_wz0(const DataMeta &m, int node) { return 1 + m.n_cols + m.n_nodes + node; }
 
 // one candidate's resolved design
 struct FitDesc {
@@ -217,6 +222,43 @@ ABN_HD void gauss_gram_acc(const DataMeta &m, const FitDesc &d, PassAcc &a)
         a.g[i] = m.G[(long long)gidx(d, i) * m.D + gy];
     }
     a.ll = m.G[gy * m.D + gy];
+    a.bad = 0;
+}
+
+// First IRLS iteration of the binomial mle from the Gram matrix: the reference starts at x = 0
+// (irls_binomial_fast_br.cpp:19), where eta = 0 for every row, hence e = 1, g = 1/2, g' = 1/4,
+// rho = g'/(g (1 - g)) = 1 exactly, W = 1/4 and W z = b' - 1/2 with b' = bp0 + y (bp1 - bp0):
+//   X'WX = X'X / 4,   X'[rho (b' - g)] = (bp0 - 1/2) X'1 + (bp1 - bp0) X'y
+// - all entries of the global Gram, so the first of the ~4-8 data passes of a fit is free.
+ABN_HD void binomial_first_acc(const DataMeta &m, const FitDesc &d, PassAcc &a)
+{
+    const int k = d.k;
+    const double dfn = (double)k / (double)m.n;
+    const double bp0 = (0.0 + dfn * 0.5) / (1 + dfn), bp1 = (1.0 + dfn * 0.5) / (1 + dfn);
+    const long long gy = gram_col(d.ycol);
+    for (int i = 0; i < k; i++) {
+        const long long gi = gidx(d, i);
+        for (int j = i; j < k; j++) a.H[tri(i, j, k)] = 0.25 * m.G[gi * m.D + gidx(d, j)];
+        a.g[i] = fma(bp1 - bp0, m.G[gi * m.D + gy], (bp0 - 0.5) * m.G[gi * m.D + 0]);
+    }
+    a.ll = -(double)m.n * 0.693147180559945309417; // loglik at eta = 0 (only used if max.iters = 1)
+    a.bad = 0;
+}
+
+// Start values of the Poisson mle (irls_poisson_fast.cpp:37-52) from precomputed moments: the
+// weights W0 = y + 0.1 depend on the child only, so X'W0X is a block of the child's weighted Gram
+// matrix Gw and X'W0z0 a column of the global Gram (virtual column gram_wz0). No data pass.
+ABN_HD void poisson_init_acc(const DataMeta &m, const FitDesc &d, int child, PassAcc &a)
+{
+    const int k = d.k;
+    const double *Gw = m.Gw + (long long)m.node_gw[child] * m.D0 * m.D0;
+    const long long gu = gram_wz0(m, child);
+    for (int i = 0; i < k; i++) {
+        const long long gi = gidx(d, i);
+        for (int j = i; j < k; j++) a.H[tri(i, j, k)] = Gw[gi * m.D0 + gidx(d, j)];
+        a.g[i] = m.G[gi * m.D + gu];
+    }
+    a.ll = 0.0;
     a.bad = 0;
 }
 

@@ -123,7 +123,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
 {
     host_log_table(); // initialise before the parallel region
     const long long n = ds->n;
-    const int D = 1 + ds->n_cols + ds->n_nodes;
+    const int D = 1 + ds->n_cols + 2 * ds->n_nodes, D0 = 1 + ds->n_cols;
     // Z = [1 | X | log(y + 0.1) of Poisson nodes], G = Z'Z
     std::vector<double> G((size_t)D * D, 0.0), lfact(ds->n_nodes, 0.0);
     std::vector<const double *> zc(D, nullptr);
@@ -131,13 +131,36 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
     std::vector<double> ones(n, 1.0);
     zc[0] = ones.data();
     for (int c = 0; c < ds->n_cols; c++) zc[1 + c] = ds->X + (size_t)c * n;
-    extra.resize(ds->n_nodes);
+    extra.resize(2 * ds->n_nodes);
+    std::vector<int> gw_index(ds->n_nodes, -1);
+    int n_pois = 0;
     for (int v = 0; v < ds->n_nodes; v++) {
         if (ds->node_family[v] != ABN_POISSON) continue;
+        gw_index[v] = n_pois++;
         const double *y = ds->X + (size_t)ds->node_col0[v] * n;
         extra[v].resize(n);
-        for (long long i = 0; i < n; i++) { extra[v][i] = std::log(y[i] + 0.1); lfact[v] += std::lgamma(y[i] + 1.0); }
+        extra[ds->n_nodes + v].resize(n);
+        for (long long i = 0; i < n; i++) {
+            const double mu = y[i] + 0.1, eta0 = std::log(mu);
+            extra[v][i] = eta0;
+            extra[ds->n_nodes + v][i] = std::fma(mu, eta0, y[i] - mu);
+            lfact[v] += std::lgamma(y[i] + 1.0);
+        }
         zc[1 + ds->n_cols + v] = extra[v].data();
+        zc[1 + ds->n_cols + ds->n_nodes + v] = extra[ds->n_nodes + v].data();
+    }
+    // weighted Gram matrices of the Poisson children: Z0' diag(y + 0.1) Z0
+    std::vector<double> Gw((size_t)std::max(1, n_pois) * D0 * D0, 0.0);
+    for (int v = 0; v < ds->n_nodes; v++) {
+        if (gw_index[v] < 0) continue;
+        const double *y = ds->X + (size_t)ds->node_col0[v] * n;
+        double *g = Gw.data() + (size_t)gw_index[v] * D0 * D0;
+        for (int a = 0; a < D0; a++)
+            for (int b = a; b < D0; b++) {
+                double s = 0.0;
+                for (long long i = 0; i < n; i++) s += (zc[a][i] * (y[i] + 0.1)) * zc[b][i];
+                g[(size_t)a * D0 + b] = g[(size_t)b * D0 + a] = s;
+            }
     }
     for (int a = 0; a < D; a++) {
         if (!zc[a]) continue;
@@ -148,7 +171,8 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             G[(size_t)a * D + b] = G[(size_t)b * D + a] = s;
         }
     }
-    DataMeta m{n, n, ds->n_nodes, ds->n_cols, D, ds->X, G.data(), ds->node_family, ds->node_col0, lfact.data()};
+    DataMeta m{n, n, ds->n_nodes, ds->n_cols, D, ds->X, G.data(), ds->node_family, ds->node_col0, lfact.data(),
+               Gw.data(), gw_index.data(), D0};
     Control c{ctrl->method, ctrl->max_iters, ctrl->solver, ctrl->nvars, ctrl->tol, ctrl->epsabs,
               ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale};
 
@@ -180,6 +204,17 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             if (c.method == BAYES) bayes_inits(m, d, child, s);
             PassAcc a;
             int mode = fit_begin(s, c);
+            if (c.method == MLE && d.family == BINOMIAL) { // as fit_kernel: iteration 1 from the Gram matrix
+                binomial_first_acc(m, d, a);
+                s.have_ll = 1;
+                mode = fit_consume(s, c, a);
+                s.passes--;
+            }
+            if (c.method == MLE && d.family == POISSON && mode == PASS_PINIT) { // start values from Gw
+                poisson_init_acc(m, d, child, a);
+                mode = fit_consume(s, c, a);
+                s.passes--;
+            }
             while (mode != PASS_DONE) {
                 if (d.family == GAUSSIAN) gauss_gram_acc(m, d, a);
                 else run_pass(m, d, c, s, mode, a);

@@ -64,11 +64,12 @@ def test_mle_ex1_config1():
         assert (np.isnan(sim[k]) == np.isnan(ref[k])).all()
     assert (sim["status"] == ref["status"]).all() and (ref["status"] == 2).sum() == 8
     fam = P.node_family[ch]
-    # passes: the IRLS iterations of the reference, plus at most one loglik-only pass when the
-    # converging iteration had not been predicted (solver.cuh PH_MLE_BIN)
+    # data passes: the IRLS iterations of the reference minus the first one (taken from the Gram
+    # matrix, plan.cuh binomial_first_acc), plus at most one loglik-only pass when the converging
+    # iteration had not been predicted (solver.cuh PH_MLE_BIN)
     b = (fam == capi.BINOMIAL) & (ref["status"] == 0)
     extra = sim["iters"][b] - ref["iters"][b]
-    assert ((extra == 0) | (extra == 1)).all() and (extra == 0).mean() > 0.5
+    assert ((extra == -1) | (extra == 0)).all() and (extra == -1).mean() > 0.5
 
 
 def test_mle_rank_deficient_binomial_drops_leading_columns():
