@@ -3,9 +3,9 @@
 // The fit kernels are bound by instruction issue and the FP64 pipe, not by HBM (ncu: profiles/):
 // libdevice's exp() / log() / IEEE division cost ~35 / ~45 / ~25 instructions each including
 // range branches and slow paths that these loops never need. The versions here cost
-//   exp   10 FP64 + 5 integer/LDS instructions   (max error 1.01 ulp, mean 0.33 ulp on |t| <= 700:
+//   exp    9 FP64 + 5 integer/LDS instructions   (max error 1.25 ulp, mean 0.34 ulp on |t| <= 700:
 //                                                 tests/test_fastmath.py against long double)
-//   rcp    1 MUFU + 6 FP64                        (correctly rounded 1/d for normal d: Markstein)
+//   rcp    1 MUFU + 5 FP64                        (correctly rounded 1/d for normal d: Markstein)
 // __host__ __device__ with identical arithmetic (FMA on both sides) so tests/host_sim.cpp
 // exercises the same bits the kernels produce, apart from the device's MUFU seed (the Newton
 // steps converge to the same correctly rounded result).
@@ -19,21 +19,30 @@
 
 namespace abn {
 
-// 2^(j/32), j = 0..31, correctly rounded (generated with 60-digit decimal arithmetic)
-#define ABN_EXP2_TABLE                                                                              \
-    {1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577,            \
-     1.1143867425958924, 1.1387886347566916, 1.1637248587775775, 1.189207115002721,                  \
-     1.215247359980469, 1.241857812073484, 1.2690509571917332, 1.2968395546510096,                   \
-     1.3252366431597413, 1.3542555469368927, 1.383909881963832, 1.4142135623730951,                  \
-     1.4451808069770467, 1.4768261459394993, 1.5091644275934228, 1.5422108254079407,                 \
-     1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429,                   \
-     1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424,                  \
-     1.8741676341103, 1.9152065613971474, 1.9571441241754002}
+// 2^(j/64), j = 0..63, correctly rounded (generated with 60-digit decimal arithmetic)
+#define ABN_EXP2_N 64
+#define ABN_EXP2_TABLE \
+    {1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, \
+     1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199, \
+     1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418, \
+     1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812, \
+     1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687, \
+     1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783, \
+     1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303, \
+     1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112, \
+     1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647, \
+     1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384, \
+     1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267, \
+     1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364, \
+     1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062, \
+     1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989, \
+     1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656, \
+     1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951}
 
 #if defined(__CUDACC__)
-__constant__ double c_exp2_table[32] = ABN_EXP2_TABLE;
+__constant__ double c_exp2_table[ABN_EXP2_N] = ABN_EXP2_TABLE;
 #endif
-static const double h_exp2_table[32] = ABN_EXP2_TABLE;
+static const double h_exp2_table[ABN_EXP2_N] = ABN_EXP2_TABLE;
 
 ABN_HD double bits_to_double(uint64_t b)
 {
@@ -57,54 +66,36 @@ ABN_HD uint64_t double_to_bits(double d)
 #endif
 }
 
-// exp(t) for |t| <= 700 (callers clamp). `tab` points at the 32-entry table: shared memory on the
+// exp(t) for |t| <= 700 (callers clamp). `tab` points at the 64-entry table: shared memory on the
 // device (lane-dependent index: a __constant__ read would serialise), h_exp2_table on the host.
-//   t = (32 k + j) ln2/32 + r,  |r| <= ln2/64;  exp(t) = 2^k * 2^(j/32) * (1 + p(r))
+//   t = (64 k + j) ln2/64 + r,  |r| <= ln2/128;  exp(t) = 2^k * 2^(j/64) * (1 + p(r))
 ABN_HD double fast_exp(double t, const double *tab)
 {
     const double MAGIC = 6755399441055744.0;        // 1.5 * 2^52: round-to-nearest-integer trick
-    const double INV = 46.16624130844683;           // 32 / ln 2
-    const double LN2_32_HI = 0.02166084938653512;   // ln2/32, low 21 mantissa bits zero: n * HI exact
-    const double LN2_32_LO = 5.9631716539705866e-12;
+    const double INV = 92.33248261689366;           // 64 / ln 2
+    const double LN2_64_HI = 0.01083042468962958;   // ln2/64, low 22 mantissa bits zero: n * HI exact
+    const double LN2_64_LO = 6.619564634077006e-12;
     const double kd = fma(t, INV, MAGIC);
-    const double nf = kd - MAGIC;                   // n = 32 k + j as a double
-    double r = fma(nf, -LN2_32_HI, t);
-    r = fma(nf, -LN2_32_LO, r);
+    const double nf = kd - MAGIC;                   // n = 64 k + j as a double
+    double r = fma(nf, -LN2_64_HI, t);
+    r = fma(nf, -LN2_64_LO, r);
     const int64_t n = (int64_t)(int32_t)(uint32_t)double_to_bits(kd); // low word of kd holds n
-    const int j = (int)(n & 31);
-    const int64_t k = n >> 5;
-    // p(r) = r + r^2/2 + r^3/6 + r^4/24 + r^5/120 + r^6/720, |r| <= 0.0109: truncation < 4e-18
-    double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
+    const int j = (int)(n & 63);
+    const int64_t k = n >> 6;
+    // p(r) = r + r^2/2 + r^3/6 + r^4/24 + r^5/120, |r| <= 0.00542: truncation < 4e-17
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
     p = fma(p, r, 1.0 / 6.0);
     p = fma(p, r, 0.5);
     p = fma(p * r, r, r);
     const double tj = tab[j];
-    const double v = fma(tj, p, tj);                // in [1, 2) * (1 +- 0.011)
+    const double v = fma(tj, p, tj);                // in [1, 2) * (1 +- 0.0055)
     return bits_to_double(double_to_bits(v) + ((uint64_t)k << 52)); // * 2^k, k in [-1010, 1010]
 }
 
-// 1 / d, correctly rounded for normal d with a normal result (Markstein: two Newton steps to
-// within an ulp, then r = fma(-d, x, 1), x + x r rounds correctly unless d's mantissa is all ones)
+// 1 / d, correctly rounded for normal d with a normal result. MUFU.RCP64H seeds ~2^-20; one step
+// with cubic convergence (x (1 + e + e^2)) lands within an ulp; then Markstein's correction
+// r = fma(-d, x, 1), x + x r rounds correctly unless d's mantissa is all ones.
 ABN_HD double fast_rcp(double d)
-{
-#if defined(__CUDA_ARCH__)
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d)); // MUFU.RCP64H, ~2^-20
-    double e = fma(-d, x, 1.0);
-    e = fma(e, e, e);               // (e + e^2): one step with cubic convergence  -> ~2^-60
-    x = fma(x, e, x);
-    e = fma(-d, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-d, x, 1.0);
-    return fma(x, e, x);
-#else
-    return 1.0 / d;
-#endif
-}
-
-// 1 / d to ~1 ulp (not necessarily correctly rounded): one Newton step less
-ABN_HD double fast_rcp_approx(double d)
 {
 #if defined(__CUDA_ARCH__)
     double x;
@@ -113,6 +104,20 @@ ABN_HD double fast_rcp_approx(double d)
     e = fma(e, e, e);
     x = fma(x, e, x);
     e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+#else
+    return 1.0 / d;
+#endif
+}
+
+// 1 / d to about an ulp (not necessarily correctly rounded): the cubic step alone
+ABN_HD double fast_rcp_approx(double d)
+{
+#if defined(__CUDA_ARCH__)
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    e = fma(e, e, e);
     return fma(x, e, x);
 #else
     return 1.0 / d;

@@ -48,7 +48,7 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // contribution of one row to the register accumulators
-template <int KIND, int K, bool ICPT, bool NEED_H, bool NEED_G, bool NEED_L>
+template <int KIND, int K, bool ICPT, bool NEED_H, bool NEED_G, bool NEED_L, bool VOTE = false>
 __device__ __forceinline__ void row_update(const double (&xd)[K], double yi, const double (&beta)[K], const RowConst &rc,
                                            double (&H)[K * (K + 1) / 2], double (&g)[K], double &ll, int &bad)
 {
@@ -57,7 +57,11 @@ __device__ __forceinline__ void row_update(const double (&xd)[K], double yi, con
 #pragma unroll
     for (int j = (ICPT ? 1 : 0); j < K; j++) eta = fma(xd[j], beta[j], eta);
     double w, r, l = 0.0;
-    RowOp<KIND>::template apply<NEED_H, NEED_G, NEED_L>(eta, yi, rc, w, r, l, bad);
+    // binomial mle: the rho correction is evaluated only when some row of this warp step needs it;
+    // VOTE is set where all 32 lanes are known to be converged (full tiles), elsewhere rho is always on
+    bool need_rho = true;
+    if (KIND == RK_BIN_MLE && VOTE && (NEED_H || NEED_G)) need_rho = __any_sync(0xffffffffu, eta >= BIN_RHO_ETA);
+    RowOp<KIND>::template apply<NEED_H, NEED_G, NEED_L>(eta, yi, rc, w, r, l, bad, need_rho);
     if (NEED_H) {
         int t = 0;
 #pragma unroll
@@ -137,7 +141,7 @@ __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const do
         }
 #pragma unroll
         for (int u = 0; u < U; u++)
-            row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L>(xc[u], yc[u], beta, rc, H, g, ll, bad);
+            row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L, true>(xc[u], yc[u], beta, rc, H, g, ll, bad);
     }
     for (long long i = n_main + lane; i < n; i += 32) { // tail: fewer than 32 * U rows
         double xt[K];
@@ -250,7 +254,7 @@ __device__ __forceinline__ void warp_pass_staged(const double *__restrict__ y, c
 #pragma unroll
             for (int j = 0; j < KD; j++) xr[j + I0] = t[j * TROWS + u * 32 + lane];
             const double yi = t[KD * TROWS + u * 32 + lane];
-            row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L>(xr, yi, beta, rc, H, g, ll, bad);
+            row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L, true>(xr, yi, beta, rc, H, g, ll, bad);
         }
         stage ^= 1;
     }
@@ -305,12 +309,12 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
 {
     __shared__ FitState st_all[FIT_WARPS];
     __shared__ PassAcc acc_all[FIT_WARPS];
-    __shared__ double exp_tab[32];
+    __shared__ double exp_tab[ABN_EXP2_N];
     __shared__ double lnmu_tab[64];
     __shared__ double log_tab[128];
     if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
     extern __shared__ double stage_tiles[]; // FIT_WARPS x FIT_STAGES x (KD+1) x 32 FIT_UNROLL (staged pass)
-    if (threadIdx.x < 32) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
+    if (threadIdx.x < ABN_EXP2_N) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
     if (KIND == RK_POIS && threadIdx.x < 64) lnmu_tab[threadIdx.x] = log((double)threadIdx.x + 0.1);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -51,9 +51,9 @@ fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ des
 {
     __shared__ MnState st_all[FIT_WARPS];
     __shared__ MnAcc acc_all[FIT_WARPS];
-    __shared__ double exp_tab[32];
+    __shared__ double exp_tab[ABN_EXP2_N];
     __shared__ double log_tab[128];
-    if (threadIdx.x < 32) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
+    if (threadIdx.x < ABN_EXP2_N) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
     if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -40,6 +40,8 @@ ABN_HD RowConst make_row_const(int k, double n, const double *tab, const double 
     return c;
 }
 
+constexpr double BIN_RHO_ETA = 12.0;
+
 ABN_HD double clamp700(double t) { return fmin(fmax(t, -700.0), 700.0); }
 
 template <int KIND>
@@ -56,8 +58,14 @@ struct RowOp<RK_BIN_MLE> {
     //   x_new = x + (X'WX)^-1 X'[rho (b' - g)]  ==  solve(X'WX, X'Wz)  (irls_binomial_fast_br.cpp:72-73)
     // with g = fl(1/(1+e)) correctly rounded like the reference's division.
     // loglik term: -y log(1+e^-eta) - (1-y) log(1+e^eta) = -log(1+e) - (1-y) eta   (:97)
+    //
+    // rho differs from 1 only through the rounding of g in 1 - g: |rho - 1| <= 2^-53 e^eta. The
+    // kernels evaluate rho only for warp steps in which some row has eta >= BIN_RHO_ETA = 12 (a
+    // warp vote); below that |rho - 1| < 2e-11 moves the coefficients by < 1e-10 of their scale,
+    // three orders under the IRLS stop tolerance, and the score by ~1e-20 - while the saturated
+    // rows, where the reference's noise is visible at 1e-8, always take the exact path.
     template <bool NEED_W, bool NEED_R, bool NEED_L>
-    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad)
+    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad, bool need_rho = true)
     {
         // The reference's W or z is non-finite when g rounds to 1 (g(1-g) = 0: 1 + e == 1, i.e.
         // eta >= 53 ln 2) or when (1+e)^2 overflows (e >= sqrt(DBL_MAX), eta <= -354.89). Outside
@@ -69,9 +77,15 @@ struct RowOp<RK_BIN_MLE> {
         if (NEED_W || NEED_R) {
             const double g = fast_rcp(d);
             const double gp = e * g * g;
-            const double rho = gp * fast_rcp_approx(g * (1.0 - g));
-            w = rho * gp;
-            r = rho * (fma(y, c.bp1 - c.bp0, c.bp0) - g);
+            const double bpg = fma(y, c.bp1 - c.bp0, c.bp0) - g;
+            if (need_rho) {
+                const double rho = gp * fast_rcp_approx(g * (1.0 - g));
+                w = rho * gp;
+                r = rho * bpg;
+            } else { // every row of this warp step has eta < BIN_RHO_ETA: |rho - 1| < 2e-11, see below
+                w = gp;
+                r = bpg;
+            }
         }
         if (NEED_L) l = -fast_log_ge1(d, c.logtab) - (1.0 - y) * eta;
     }
@@ -80,7 +94,7 @@ struct RowOp<RK_BIN_MLE> {
 template <>
 struct RowOp<RK_POIS> {
     template <bool NEED_W, bool NEED_R, bool NEED_L>
-    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad)
+    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad, bool need_rho = true)
     {
         bad |= !(eta < 709.782712893384); // exp(eta) = +Inf (or eta is NaN) in the reference
         const double E = fast_exp(fmax(eta, -700.0), c.tab); // flagged fits never use E; no upper clamp
@@ -96,7 +110,7 @@ struct RowOp<RK_BIN_BAYES> {
     // hessian weight exp(eta - 2 log(1+E)) = sigma/(1+E) (:761-764), log term log(1+E) (eta if E
     // overflows, :633-639). For |eta| > 700 the clamped E gives the same doubles as those branches.
     template <bool NEED_W, bool NEED_R, bool NEED_L>
-    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad)
+    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad, bool need_rho = true)
     {
         const double E = fast_exp(clamp700(eta), c.tab);
         const double d = 1.0 + E;
@@ -108,6 +122,7 @@ struct RowOp<RK_BIN_BAYES> {
         }
         if (NEED_L) l = (eta > 700.0) ? (y * eta - eta) : (y * eta - fast_log_ge1(d, c.logtab));
         (void)bad;
+        (void)need_rho;
     }
 };
 
@@ -117,7 +132,7 @@ struct RowOp<RK_PINIT> {
     // H = X'W0X, g = X'W0z0 with W0 z0 = W0 eta0 + (y - W0): no division needed. Counts are small
     // integers, so log(y + 0.1) comes from a 64-entry table; other values take the libm path.
     template <bool NEED_W, bool NEED_R, bool NEED_L>
-    static ABN_HD void apply(double, double y, const RowConst &c, double &w, double &r, double &l, int &bad)
+    static ABN_HD void apply(double, double y, const RowConst &c, double &w, double &r, double &l, int &bad, bool need_rho = true)
     {
         const double mu = y + 0.1;
         const int yi = (int)y;

@@ -46,9 +46,11 @@ void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode
             eta = std::fma(x[j], beta[j], eta);
         }
         double w = 0.0, r = 0.0, l = 0.0;
-        if (need_l && (need_h || need_g)) RowOp<KIND>::template apply<true, true, true>(eta, y[i], rc, w, r, l, a.bad);
-        else if (need_l) RowOp<KIND>::template apply<false, false, true>(eta, y[i], rc, w, r, l, a.bad);
-        else RowOp<KIND>::template apply<true, true, false>(eta, y[i], rc, w, r, l, a.bad);
+        // the kernels decide per warp step (vote) whether rho is evaluated; row by row here
+        const bool need_rho = eta >= BIN_RHO_ETA;
+        if (need_l && (need_h || need_g)) RowOp<KIND>::template apply<true, true, true>(eta, y[i], rc, w, r, l, a.bad, need_rho);
+        else if (need_l) RowOp<KIND>::template apply<false, false, true>(eta, y[i], rc, w, r, l, a.bad, need_rho);
+        else RowOp<KIND>::template apply<true, true, false>(eta, y[i], rc, w, r, l, a.bad, need_rho);
         if (need_h)
             for (int p = 0; p < k; p++)
                 for (int q = p; q < k; q++) a.H[tri(p, q, k)] += w * x[p] * x[q];
