@@ -579,8 +579,12 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
         for (int b = 0; b < NBUCKETS; b++) {
             const int count = hstart[b + 1] - hstart[b];
             if (count <= 0) continue;
+            // pass 0: the Gram-only Gaussian kernel (largest per-thread stack: launching it first
+            // keeps the one-off local-memory pool resize from synchronising with running kernels) and
+            // the small buckets on side streams; pass 1: the large buckets on the main stream
             const bool small = (b >= 2) && count < small_limit;
-            if ((pass == 0) != small) continue;
+            const bool early = small || b <= 1;
+            if ((pass == 0) != early) continue;
             cudaStream_t ks = small ? d->side[n_side++ % abn_data::NSIDE] : s;
             const bool timed = (b >= 1 && (int)kid.size() < ABN_MAX_KERNELS);
             cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -603,7 +607,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
                 else if (fam == 1) fn = get_launch_pois(k, icpt);
                 else mfn = get_launch_mn(fam, k, icpt);
                 if (mfn) {
-                    int grid = std::min((count + FIT_WARPS - 1) / FIT_WARPS, d->sm_count);
+                    int grid = std::min((count + FIT_WARPS - 1) / FIT_WARPS, d->sm_count * 2);
                     mfn(d->m, c, d->dDescs, list, count, d->dCounters + b, rp, grid, ks);
                 } else if (!fn) {
                     n_unsupported += count;

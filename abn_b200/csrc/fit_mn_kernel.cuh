@@ -11,20 +11,64 @@
 
 namespace abn {
 
+constexpr int MN_UNROLL = 2;
+
+template <int L, int K, bool ICPT>
+constexpr size_t mn_stage_bytes()
+{
+    return (size_t)FIT_WARPS * FIT_STAGES * (K - (ICPT ? 1 : 0) + L - 1) * 32 * MN_UNROLL * sizeof(double);
+}
+
+// same cp.async staging as warp_pass_staged (fit_kernel.cuh): each lane copies and reads back only
+// its own rows; staged columns = the design columns plus the L-1 indicator columns of the child
 template <int L, int K, bool ICPT>
 __device__ __forceinline__ void mn_warp_pass(const double *__restrict__ y0, long long ld, const double *const (&cp)[MAXK],
-                                             const double *w_sm, long long n, const double *tab, const double *logtab, MnAcc *acc_sm)
+                                             const double *w_sm, long long n, const double *tab, const double *logtab,
+                                             MnAcc *acc_sm, double *tile)
 {
     constexpr int KD = K - (ICPT ? 1 : 0);
     constexpr int I0 = ICPT ? 1 : 0;
     constexpr int NP = (L - 1) * K;
+    constexpr int U = MN_UNROLL;
+    constexpr int NC = KD + L - 1;
+    constexpr int TROWS = 32 * U;
     const int lane = threadIdx.x & 31;
     double W[NP], g[NP], f = 0.0;
 #pragma unroll
     for (int i = 0; i < NP; i++) { W[i] = w_sm[i]; g[i] = 0.0; }
     int bad = 0;
-#pragma unroll 2
-    for (long long i = lane; i < n; i += 32) {
+    const long long n_main = (n / TROWS) * TROWS;
+    auto issue = [&](long long base, int stage) {
+        double *t = tile + (size_t)stage * NC * TROWS;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int j = 0; j < KD; j++) cp_async8(t + j * TROWS + u * 32 + lane, cp[j] + base + u * 32 + lane);
+#pragma unroll
+            for (int l = 1; l < L; l++) cp_async8(t + (KD + l - 1) * TROWS + u * 32 + lane, y0 + (long long)l * ld + base + u * 32 + lane);
+        }
+        cp_async_commit();
+    };
+    if (n_main > 0) issue(0, 0);
+    int stage = 0;
+    for (long long base = 0; base < n_main; base += TROWS) {
+        const long long nb = base + TROWS;
+        if (nb < n_main) { issue(nb, stage ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        const double *t = tile + (size_t)stage * NC * TROWS;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            double x[K], yl[L - 1];
+            if (ICPT) x[0] = 1.0;
+#pragma unroll
+            for (int j = 0; j < KD; j++) x[j + I0] = t[j * TROWS + u * 32 + lane];
+#pragma unroll
+            for (int l = 1; l < L; l++) yl[l - 1] = t[(KD + l - 1) * TROWS + u * 32 + lane];
+            mn_row<L, K, ICPT>(x, yl, W, tab, logtab, f, g);
+        }
+        stage ^= 1;
+    }
+    for (long long i = n_main + lane; i < n; i += 32) {
         double x[K], yl[L - 1];
         if (ICPT) x[0] = 1.0;
 #pragma unroll
@@ -45,7 +89,7 @@ __device__ __forceinline__ void mn_warp_pass(const double *__restrict__ y0, long
 }
 
 template <int L, int K, bool ICPT>
-__global__ void __launch_bounds__(FIT_WARPS * 32, 1)
+__global__ void __launch_bounds__(FIT_WARPS * 32, (L - 1) * K <= 16 ? 2 : 1)
 fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ list,
               int count, int *counter, ResultPtrs out)
 {
@@ -56,9 +100,11 @@ fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ des
     if (threadIdx.x < ABN_EXP2_N) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
     if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
     __syncthreads();
+    extern __shared__ double stage_tiles[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     MnState &st = st_all[warp];
     MnAcc *acc = &acc_all[warp];
+    double *tile = stage_tiles + (size_t)warp * FIT_STAGES * (K - (ICPT ? 1 : 0) + L - 1) * 32 * MN_UNROLL;
     for (;;) {
         int idx = 0;
         if (lane == 0) idx = atomicAdd(counter, 1);
@@ -82,7 +128,7 @@ fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ des
         more = __shfl_sync(0xffffffffu, more, 0);
         __syncwarp();
         while (more) {
-            mn_warp_pass<L, K, ICPT>(y0, m.ld, cp, st.b, m.n, exp_tab, log_tab, acc);
+            mn_warp_pass<L, K, ICPT>(y0, m.ld, cp, st.b, m.n, exp_tab, log_tab, acc, tile);
             __syncwarp();
             if (lane == 0) more = mn_consume(st, *acc) ? 1 : 0;
             more = __shfl_sync(0xffffffffu, more, 0);
@@ -107,7 +153,13 @@ template <int L, int K, bool ICPT>
 void launch_mn(const DataMeta &m, const Control &c, const FitDesc *descs, const int *list, int count, int *counter,
                ResultPtrs out, int grid, cudaStream_t stream)
 {
-    fit_mn_kernel<L, K, ICPT><<<grid, FIT_WARPS * 32, 0, stream>>>(m, c, descs, list, count, counter, out);
+    constexpr size_t smem = mn_stage_bytes<L, K, ICPT>();
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(fit_mn_kernel<L, K, ICPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    fit_mn_kernel<L, K, ICPT><<<grid, FIT_WARPS * 32, smem, stream>>>(m, c, descs, list, count, counter, out);
 }
 
 MnLaunchFn get_launch_mn(int L, int k, int icpt); // fit_table.cu

@@ -611,6 +611,19 @@ ABN_HDN int fit_begin(FitState &s, const Control &c)
     return PASS_HG;
 }
 
+// Pass a Poisson-mle trial point needs: when the step to it is already shorter than the stop
+// tolerance (or the iteration cap is reached) the trial can only end the fit - accepted it
+// converges (irls_poisson_fast.cpp:129), rejected the next half step is shorter still - so only
+// its log-likelihood is needed, not the Gram sums.
+ABN_HD int pois_trial_mode(FitState &s, const Control &c)
+{
+    double nrm = 0.0;
+    for (int i = 0; i < s.k; i++) { double d = s.x[i] - s.xold[i]; nrm += d * d; }
+    const bool last = (sqrt(nrm) < c.tol) || (s.iters >= c.max_iters);
+    s.have_ll = last ? 2 : 1; // 2: the pass in flight has no H / g
+    return last ? PASS_LL : PASS_FULL;
+}
+
 ABN_HD void mle_scores(FitState &s, double ll, double df)
 {
     s.loglik = ll;
@@ -701,7 +714,7 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
                         fin = true;
                         for (int i = 0; i < k; i++) { s.x[i] = s.xold[i] + s.step * s.dir[i]; if (!isfinite(s.x[i])) fin = false; }
                     }
-                    if (fin && s.halvings < 10) return PASS_FULL;
+                    if (fin && s.halvings < 10) return pois_trial_mode(s, c);
                 }
                 // no valid step: revert, norm(x - xold) = 0 < tol -> stop (:122-131); ll stays cur_ll
                 for (int i = 0; i < k; i++) s.x[i] = s.xold[i];
@@ -713,6 +726,12 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
             for (int i = 0; i < k; i++) { double d = s.x[i] - s.xold[i]; nrm += d * d; }
             if (sqrt(nrm) < c.tol) { mle_scores(s, ll_here, (double)k); return PASS_DONE; } // final ll :137 at the same x
             if (s.iters >= c.max_iters) { s.status = FIT_NOT_CONVERGED; mle_scores(s, ll_here, (double)k); return PASS_DONE; }
+            if (s.have_ll == 2) { // cannot happen (same norm as pois_trial_mode); be safe: redo the point in full
+                s.phase = PH_POIS_FIRST;
+                s.iters--;
+                s.have_ll = 1;
+                return PASS_FULL;
+            }
         }
         // next IRLS iteration from s.x with this pass's sums (:62-91)
         if (s.phase == PH_POIS_FIRST && c.max_iters <= 0) { mle_scores(s, ll_here, (double)k); return PASS_DONE; }
@@ -749,7 +768,7 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
             return PASS_DONE;
         }
         s.phase = PH_POIS_TRIAL;
-        return PASS_FULL;
+        return pois_trial_mode(s, c);
     }
     case PH_NEWTON: {
         double f[MAXM], step[MAXM];
