@@ -18,7 +18,8 @@ BINOMIAL, GAUSSIAN, POISSON, MULTINOMIAL = 1, 2, 3, 4
 METHOD_MLE, METHOD_BAYES = 0, 1
 SOLVER_NEWTON, SOLVER_HYBRID = 0, 1
 FIT_OK, FIT_NOT_CONVERGED, FIT_NON_FINITE = 0, 1, 2
-MAX_K = 8
+MAX_K = 32   # widest design
+FAST_K = 8   # widest design of the register-resident kernels
 MAX_KERNELS = 64
 
 FAMILY_CODE = {"binomial": BINOMIAL, "gaussian": GAUSSIAN, "poisson": POISSON, "multinomial": MULTINOMIAL}

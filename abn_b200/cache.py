@@ -210,11 +210,13 @@ def node_defn(children0, parents, d):
 
 def kernel_name(kid: int) -> str:
     """Readable name of abn_timing.kernel_id."""
+    if kid == 0:
+        return "fit_wide_kernel"
     if kid == 1:
         return "gauss_kernel"
     code = kid - 2
     icpt, fk = code & 1, code >> 1
-    fam, k = divmod(fk, capi.MAX_K + 1)
+    fam, k = divmod(fk, capi.FAST_K + 1)
     if fam >= 2:
         return f"fit_mn_kernel<L={fam},K={k},icpt={icpt}>"
     return f"fit_kernel<{('binomial', 'poisson')[fam]},K={k},icpt={icpt}>"

@@ -18,7 +18,13 @@
 
 using namespace abn;
 
-static_assert(ABN_MAX_K == MAXK, "include/abn_b200.h and solver.cuh disagree on the design width");
+// wide.cu: generic kernel for designs of 9..32 columns
+cudaError_t abn_wide_launch(const abnc::DataMeta &m, const abnc::Control &c, const int *child, const int *parents,
+                            int width, const int *list, int count, int *counter, abnc::ResultPtrs out, int sm_count,
+                            cudaStream_t stream);
+int abn_wide_max_k();
+
+static_assert(ABN_FAST_K == MAXK, "include/abn_b200.h and solver.cuh disagree on the fast-path design width");
 static_assert(MN_MAXL == MN_MAXL_, "plan.cuh and solver_mn.cuh disagree on the multinomial level limit");
 
 // ---------------------------------------------------------------------------------------------
@@ -586,7 +592,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
             const bool early = small || b <= 1;
             if ((pass == 0) != early) continue;
             cudaStream_t ks = small ? d->side[n_side++ % abn_data::NSIDE] : s;
-            const bool timed = (b >= 1 && (int)kid.size() < ABN_MAX_KERNELS);
+            const bool timed = ((int)kid.size() < ABN_MAX_KERNELS);
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (timed) {
                 CUDA_TRY(cudaEventCreate(&e0));
@@ -595,8 +601,10 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
             }
             const int *list = d->dIdxSorted + hstart[b];
             if (b == 0) {
-                n_unsupported = count;
-                unsupported_kernel<<<(count + 255) / 256, 256, 0, ks>>>(list, count, rp);
+                // not for the register-resident kernels: wider than 8 columns (-> generic wide kernel,
+                // which re-resolves the design with its own limit and flags what it cannot take)
+                CUDA_TRY(abn_wide_launch(d->m, c, d->dChild, d->dParents, width, list, count, d->dCounters + b, rp,
+                                         d->sm_count, ks));
             } else if (b == 1) {
                 gauss_kernel<<<(count + 127) / 128, 128, 0, ks>>>(d->m, c, d->dDescs, d->dChild, list, count, rp);
             } else {
@@ -696,7 +704,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     for (auto &e : kev1) cudaEventDestroy(e);
     for (auto &e : ev) cudaEventDestroy(e);
     if (n_unsupported > 0 && n_unsupported == rows)
-        return fail(err, errlen, ABN_ERR_LIMIT, "no candidate could be scored: designs wider than %d columns or multinomial children are not supported by this build", MAXK);
+        return fail(err, errlen, ABN_ERR_LIMIT, "no candidate could be scored by the fast kernels");
     return ABN_OK;
 }
 

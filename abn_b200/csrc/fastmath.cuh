@@ -17,7 +17,7 @@
 
 #include "solver.cuh"
 
-namespace abn {
+namespace ABN_NS {
 
 // 2^(j/64), j = 0..63, correctly rounded (generated with 60-digit decimal arithmetic)
 #define ABN_EXP2_N 64
@@ -155,4 +155,4 @@ ABN_HD double fast_log_ge1(double x, const double *tab)
     return fma(ed, LN2_HI, tab[2 * i + 1] + fma(ed, LN2_LO, p));
 }
 
-} // namespace abn
+} // namespace ABN_NS

@@ -20,12 +20,7 @@
 #include "rowops.cuh"
 #include "solver.cuh"
 
-namespace abn {
-
-struct ResultPtrs {
-    double *mlik, *aic, *bic, *mdl;
-    int *status, *iters;
-};
+namespace ABN_NS {
 
 // tunables (overridable at build time for sweeps: make EXTRA="-DABN_FIT_WARPS=.. -DABN_MIN_BLOCKS=.. -DABN_UNROLL=..")
 #ifndef ABN_FIT_WARPS
@@ -409,4 +404,4 @@ FitLaunchFn get_launch_bin_mle(int k, int icpt);
 FitLaunchFn get_launch_bin_bayes(int k, int icpt);
 FitLaunchFn get_launch_pois(int k, int icpt);
 
-} // namespace abn
+} // namespace ABN_NS

@@ -9,7 +9,7 @@
 #include "rowops_mn.cuh"
 #include "solver_mn.cuh"
 
-namespace abn {
+namespace ABN_NS {
 
 constexpr int MN_UNROLL = 2;
 
@@ -164,4 +164,4 @@ void launch_mn(const DataMeta &m, const Control &c, const FitDesc *descs, const 
 
 MnLaunchFn get_launch_mn(int L, int k, int icpt); // fit_table.cu
 
-} // namespace abn
+} // namespace ABN_NS

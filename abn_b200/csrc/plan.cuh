@@ -11,23 +11,7 @@
 
 #include "solver.cuh"
 
-namespace abn {
-
-// device-resident description of the data set
-struct DataMeta {
-    long long n;     // observations
-    long long ld;    // leading dimension (elements) of the column-major matrix
-    int n_nodes, n_cols;
-    int D;           // Gram dimension = 1 + n_cols + 2 n_nodes
-    const double *X; // column-major, ld x n_cols
-    const double *G; // D x D row-major symmetric
-    const int *node_family; // [n_nodes]
-    const int *node_col0;   // [n_nodes + 1]
-    const double *node_lfact; // [n_nodes] sum lgamma(y + 1) (Poisson nodes, else 0)
-    const double *Gw;         // per Poisson node: Z0' diag(y + 0.1) Z0, Z0 = [1 | X], D0 x D0 each
-    const int *node_gw;       // [n_nodes] ordinal of the node's block in Gw, -1 if not Poisson
-    int D0;                   // 1 + n_cols
-};
+namespace ABN_NS {
 
 ABN_HD int gram_icpt() { return 0; }
 ABN_HD int gram_col(int c) { return 1 + c; }
@@ -63,7 +47,7 @@ ABN_HD int bucket_of(const FitDesc &d)
     return 2 + (fam * (MAXK + 1) + d.k) * 2 + icpt;
 }
 constexpr int NBUCKETS = 2 + NFAMSLOT * (MAXK + 1) * 2;
-static_assert(NBUCKETS <= 256, "bucket keys are bytes");
+static_assert(MAXK > 8 || NBUCKETS <= 256, "bucket keys are bytes (the wide build does not bucket)");
 
 ABN_HD int gidx(const FitDesc &d, int j) { return d.cols[j] < 0 ? 0 : 1 + d.cols[j]; }
 
@@ -278,4 +262,4 @@ ABN_HD double mdl_of(double bic, const FitDesc &d, int nvars)
     return bic + (double)(1 + d.kdata - d.num_na) * log((double)nvars);
 }
 
-} // namespace abn
+} // namespace ABN_NS

@@ -11,7 +11,7 @@
 #include "fastmath.cuh"
 #include "solver.cuh"
 
-namespace abn {
+namespace ABN_NS {
 
 enum RowKind : int {
     RK_BIN_MLE = 0,   // src/irls_binomial_fast_br.cpp:53-66,97
@@ -146,4 +146,4 @@ struct RowOp<RK_PINIT> {
     }
 };
 
-} // namespace abn
+} // namespace ABN_NS

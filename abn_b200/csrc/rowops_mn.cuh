@@ -4,7 +4,7 @@
 #include "fastmath.cuh"
 #include "solver.cuh"
 
-namespace abn {
+namespace ABN_NS {
 
 // value and gradient contribution of one row. x: design row (x[0] = 1 with ICPT), yl[l-1] = one-hot
 // indicator of level l (l = 1..L-1; level 0 is the reference), W: (L-1) x K weights.
@@ -40,4 +40,4 @@ ABN_HD void mn_row(const double (&x)[K], const double (&yl)[L - 1], const double
     }
 }
 
-} // namespace abn
+} // namespace ABN_NS

@@ -31,9 +31,24 @@
 #define ABN_HDN inline
 #endif
 
-namespace abn {
+#include "types.cuh"
 
-constexpr int MAXK = 8;        // widest streamed design (intercept + data columns)
+// The same headers build twice: namespace abn with MAXK = 8 (register-resident accumulators, the
+// fast path) and namespace abnw with MAXK = 32 (wide.cu: generic kernel for wider designs).
+#ifndef ABN_MAXK
+#define ABN_MAXK 8
+#endif
+#ifndef ABN_NS
+#define ABN_NS abn
+#endif
+
+namespace ABN_NS {
+
+using abnc::Control;
+using abnc::DataMeta;
+using abnc::ResultPtrs;
+
+constexpr int MAXK = ABN_MAXK; // widest design (intercept + data columns)
 constexpr int MAXM = MAXK + 1; // unknowns of the root problem (Gaussian Bayes adds the precision)
 constexpr int NTRI = MAXK * (MAXK + 1) / 2;
 
@@ -51,11 +66,6 @@ enum PassMode : int {
     PASS_PINIT = 4,  // Poisson MLE start values: H = X'W0X, g = X'W0z0 (irls_poisson_fast.cpp:37-52)
     PASS_HG = 5,     // H and g, no log-likelihood term (saves the log per row)
     PASS_LL = 6      // log-likelihood term only
-};
-
-struct Control {
-    int method, max_iters, solver, nvars;
-    double tol, epsabs, prior_mean, prior_sd, gam_shape, gam_scale;
 };
 
 // raw reductions of one pass; H is the packed upper triangle, row-major: (a,b), a <= b
@@ -898,4 +908,4 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
     return PASS_DONE;
 }
 
-} // namespace abn
+} // namespace ABN_NS

@@ -14,7 +14,7 @@
 
 #include "solver.cuh"
 
-namespace abn {
+namespace ABN_NS {
 
 constexpr int MN_MAXL = 5;                       // levels of a multinomial child handled on the GPU
 constexpr int MN_MAXP = (MN_MAXL - 1) * MAXK;    // free weights
@@ -182,4 +182,4 @@ ABN_HDN bool mn_consume(MnState &s, const MnAcc &a)
     return false;
 }
 
-} // namespace abn
+} // namespace ABN_NS

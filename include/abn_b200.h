@@ -78,11 +78,13 @@ enum {
     ABN_ERR_ARG = -1,     /* bad argument (message says which)                            */
     ABN_ERR_CUDA = -2,    /* CUDA runtime error (message carries cudaGetErrorString)      */
     ABN_ERR_NO_GPU = -3,  /* no CUDA device / kernel image not loadable - there is no CPU path */
-    ABN_ERR_LIMIT = -4,   /* design wider than ABN_MAX_K columns                           */
+    ABN_ERR_LIMIT = -4,   /* nothing could be scored (designs wider than ABN_MAX_K columns ...)  */
     ABN_ERR_ALLOC = -5
 };
 
-#define ABN_MAX_K 8 /* widest design matrix (intercept + expanded parent columns) this build streams */
+#define ABN_MAX_K 32 /* widest design matrix (intercept + expanded parent columns); designs of up to
+                       ABN_FAST_K columns run in the register-resident kernels, wider ones in a generic kernel */
+#define ABN_FAST_K 8
 
 /*
  * The data set, already prepared as the R drivers prepare it before their loops
@@ -197,8 +199,8 @@ typedef struct abn_timing {
     int64_t algo_bytes; /* sum over fits of passes * n * (k_data + 1) * 8         */
     int32_t n_kernels;  /* fit kernels launched by the call, entries used below              */
     int32_t reserved;
-    int32_t kernel_id[ABN_MAX_KERNELS];    /* 1 = Gram-only Gaussian kernel; otherwise
-                                              2 + ((family_idx * (ABN_MAX_K+1) + k) * 2 + intercept),
+    int32_t kernel_id[ABN_MAX_KERNELS];    /* 0 = generic wide kernel; 1 = Gram-only Gaussian kernel; otherwise
+                                              2 + ((family_idx * (ABN_FAST_K+1) + k) * 2 + intercept),
                                               family_idx 0 = binomial, 1 = Poisson, L = 2..5:
                                               multinomial child with L levels               */
     int64_t kernel_fits[ABN_MAX_KERNELS];

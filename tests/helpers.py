@@ -55,28 +55,30 @@ def control(method, d, **kw):
     return abncache.to_c_control(ctrl, method, d)
 
 
-_sim = None
+_sim = {}
 
 
-def sim_lib():
-    global _sim
-    if _sim is None:
-        path = os.path.join(HERE, "libhost_sim.so")
+def sim_lib(wide=False):
+    key = "wide" if wide else "narrow"
+    if key not in _sim:
+        path = os.path.join(HERE, "libhost_sim_wide.so" if wide else "libhost_sim.so")
         subprocess.run(["make", "-s", "-C", HERE], check=True, capture_output=True)
-        _sim = C.CDLL(path)
-        _sim.sim_score_cache.argtypes = [C.POINTER(capi.Dataset), C.POINTER(capi.Candidates), C.POINTER(capi.Control),
-                                         C.POINTER(capi.Result), C.POINTER(C.c_int)]
-        _sim.sim_score_cache.restype = C.c_int
-    return _sim
+        lib = C.CDLL(path)
+        lib.sim_score_cache.argtypes = [C.POINTER(capi.Dataset), C.POINTER(capi.Candidates), C.POINTER(capi.Control),
+                                        C.POINTER(capi.Result), C.POINTER(C.c_int)]
+        lib.sim_score_cache.restype = C.c_int
+        _sim[key] = lib
+    return _sim[key]
 
 
-def sim_score(P: prep.Prepared, children0, parents, ctrl):
-    """The product's solver state machines driven on the CPU (tests/host_sim.cpp)."""
+def sim_score(P: prep.Prepared, children0, parents, ctrl, wide=False):
+    """The product's solver state machines driven on the CPU (tests/host_sim.cpp); wide=True uses the
+    MAXK = 32 build of the same headers (the limits of abn_b200/csrc/wide.cu)."""
     ds, k1 = capi.make_dataset(P.X, P.node_family, P.node_col0)
     cd, k2 = capi.make_candidates(children0, parents)
     res, arrs = capi.make_result(cd.rows, ctrl.method)
     buckets = np.zeros(max(1, cd.rows), dtype=np.intc)
-    rc = sim_lib().sim_score_cache(C.byref(ds), C.byref(cd), C.byref(ctrl), C.byref(res),
+    rc = sim_lib(wide).sim_score_cache(C.byref(ds), C.byref(cd), C.byref(ctrl), C.byref(res),
                                    buckets.ctypes.data_as(C.POINTER(C.c_int)))
     assert rc == 0
     arrs["bucket"] = buckets[:cd.rows]

@@ -16,7 +16,7 @@
 #include "../abn_b200/csrc/solver_mn.cuh"
 #include "../include/abn_b200.h"
 
-using namespace abn;
+using namespace ABN_NS;
 
 namespace {
 
@@ -186,7 +186,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
         if (buckets) buckets[r] = bucket_of(d);
         double ll = NAN, aic = NAN, bic = NAN, mdl = NAN;
         int status = FIT_NON_FINITE, passes = 0;
-        if (d.err || d.k == 0 || (d.family == MULTINOMIAL && (d.nlev < 2 || d.nlev > MN_MAXL || c.method != MLE))) {
+        if (d.err || d.k == 0 || (d.family == MULTINOMIAL && (d.nlev < 2 || d.nlev > MN_MAXL || c.method != MLE || d.k > 8))) {
             // not supported by this build
         } else if (d.family == MULTINOMIAL) {
             MnState s;

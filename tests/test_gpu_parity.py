@@ -191,3 +191,41 @@ def test_multinomial_child_and_parent_config5_small():
         # nnet's BFGS stops on reltol 1e-8 of the objective: parity unpinned beyond that
         assert H.rel_err(res[k][m_child], ref[k][m_child]).max() < 1e-7, k
         assert H.rel_err(res[k][~m_child], ref[k][~m_child]).max() < TOL, k
+
+
+@pytest.mark.parametrize("method", ["mle", "bayes"])
+def test_wide_designs_generic_kernel(method):
+    """9..12 design columns: the generic kernel of wide.cu (same solver headers, MAXK = 32)."""
+    names, data, dists, _, _ = synth.make_config(4, n=3000, n_nodes=14)
+    d = len(names)
+    P = prep.prepare(data, dists, method)
+    rng = np.random.default_rng(4)
+    ch, par = [], []
+    for child in range(9):
+        for size in (3, 8, 9, 11):
+            others = [i for i in range(d) if i != child]
+            ps = sorted(rng.choice(others, size=size, replace=False))
+            ch.append(child)
+            par.append(ps + [-1] * (11 - size))
+    ch, par = np.array(ch, np.int32), np.array(par, np.int32)
+    ctrl = H.control(method, d)
+    res = H.gpu_score(P, ch, par, ctrl)
+    ref = H.oracle_score(P, ch, par, ctrl)
+    assert (res["status"] == ref["status"]).all()
+    for k in (("mlik", "aic", "bic", "mdl") if method == "mle" else ("mlik",)):
+        assert H.rel_err(res[k], ref[k]).max() < TOL, k
+
+
+def test_four_family_fixture_full_cache_runs():
+    """tests/testthat/test-build_score_cache_mle.R:300-324 (expect_no_error): 8 nodes of all four
+    families incl. two 3-level multinomial nodes, max.parents = 7 -> designs up to 12 columns, rank-
+    deficient one-hot blocks, multinomial children. Must not crash; every row gets a status."""
+    z = H.load_npz("four_family_250.npz")
+    names, data = H.df_from_npz(z)
+    dists = H.dists_from_npz(z)
+    cache = abncache.buildScoreCache(data, dists, method="mle", max_parents=7)
+    rows = 8 * 2 ** 7
+    assert len(cache["mlik"]) == rows and cache["node.defn"].shape == (rows, 8)
+    assert set(np.unique(cache.status)) <= {0, 1, 2}
+    assert (cache.status == 0).mean() > 0.5
+    assert np.isfinite(cache["mlik"][cache.status == 0]).all()

@@ -145,3 +145,28 @@ def test_multinomial_child_vmmin_state_machine():
     # children with the multinomial parent (4 one-hot columns, no intercept) stay at 1e-9
     others = ~m_child
     assert H.rel_err(sim["mlik"][others], ref["mlik"][others]).max() < 1e-9
+
+
+@pytest.mark.parametrize("method", ["mle", "bayes"])
+def test_wide_designs_up_to_12_columns(method):
+    """Designs wider than 8 columns go to the generic kernel of abn_b200/csrc/wide.cu, which builds the
+    same headers with MAXK = 32; here its state machines run on the CPU against the oracle."""
+    names, data, dists, _, _ = synth.make_config(4, n=1500, n_nodes=14)
+    d = len(names)
+    P = prep.prepare(data, dists, method)
+    rng = np.random.default_rng(4)
+    ch, par = [], []
+    for child in range(6):
+        for size in (8, 9, 11):
+            others = [i for i in range(d) if i != child]
+            ps = sorted(rng.choice(others, size=size, replace=False))
+            ch.append(child)
+            par.append(ps + [-1] * (11 - size))
+    ch, par = np.array(ch, np.int32), np.array(par, np.int32)
+    ctrl = H.control(method, d)
+    sim = H.sim_score(P, ch, par, ctrl, wide=True)
+    ref = H.oracle_score(P, ch, par, ctrl)
+    assert (sim["status"] == ref["status"]).all()
+    assert H.rel_err(sim["mlik"], ref["mlik"]).max() < 1e-9
+    narrow = H.sim_score(P, ch, par, ctrl)         # the MAXK = 8 build refuses them
+    assert (narrow["status"] == 2).all() and np.isnan(narrow["mlik"]).all()
