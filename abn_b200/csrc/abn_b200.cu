@@ -94,9 +94,12 @@ __device__ __forceinline__ double z_value(const DataMeta &m, int a, long long i)
 // memory (row-major, padded) and every thread sweeps them. Partial tiles go to
 // part[chunk][pair][GT*GT]; gram_reduce sums the chunks in a fixed order.
 __global__ void __launch_bounds__(GRAM_THREADS)
-gram_partial(const DataMeta m, int Dz, int wnode, int T, int NP, int RC, int Dp, long long rows_per_chunk,
-             double *__restrict__ part)
+gram_partial(const DataMeta m, int Dz, const int *__restrict__ wnodes, int T, int NP, int RC, int Dp,
+             long long rows_per_chunk, double *__restrict__ part)
 {
+    // blockIdx.z selects one of several weighted Gram matrices computed by the same launch
+    const int wnode = wnodes ? wnodes[blockIdx.z] : -1;
+    part += (long long)blockIdx.z * gridDim.x * NP * (GT * GT);
     // Dz: columns of Z used (m.D for the global Gram, m.D0 for a weighted one); wnode >= 0: weight
     // rows by (y_wnode + 0.1) (the Poisson mle start weights of child wnode)
     extern __shared__ double zs[]; // RC x Dp, then RC weights
@@ -156,6 +159,8 @@ gram_partial(const DataMeta m, int Dz, int wnode, int T, int NP, int RC, int Dp,
 
 __global__ void gram_reduce(int D, int T, int NP, int chunks, const double *__restrict__ part, double *__restrict__ G)
 {
+    part += (long long)blockIdx.y * chunks * NP * (GT * GT);
+    G += (long long)blockIdx.y * D * D;
     const int e = blockIdx.x * blockDim.x + threadIdx.x; // element of a tile pair
     if (e >= NP * GT * GT) return;
     const int pair = e / (GT * GT), st = e - pair * (GT * GT);
@@ -314,9 +319,9 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
     delete d;
 }
 
-// one Gram matrix: Dz columns of Z, optional row weights (y_wnode + 0.1), result Dz x Dz at dst
-static int launch_gram(abn_data *d, int Dz, int wnode, double *dst, double **part_io, size_t *part_cap,
-                       char *err, size_t errlen)
+// nmat Gram matrices in one launch: Dz columns of Z; matrix z is weighted by (y_wnodes[z] + 0.1)
+// (wnodes == nullptr: one unweighted matrix); results Dz x Dz each, consecutive at dst
+static int launch_gram(abn_data *d, int Dz, const int *wnodes, int nmat, double *dst, char *err, size_t errlen)
 {
     const DataMeta &m = d->m;
     const int T = (Dz + GT - 1) / GT;
@@ -327,24 +332,25 @@ static int launch_gram(abn_data *d, int Dz, int wnode, double *dst, double **par
     if ((size_t)RC * (Dp + 1) * sizeof(double) > 200 * 1024)
         return fail(err, errlen, ABN_ERR_LIMIT, "data set has too many columns for the Gram kernel (D=%d)", Dz);
     const int gy = (NP + GRAM_THREADS - 1) / GRAM_THREADS;
-    int chunks = std::max(1, (2 * d->sm_count) / gy);
+    int chunks = std::max(1, (2 * d->sm_count) / (gy * nmat));
+    if (nmat > 1) chunks = std::max(chunks, 16);
     long long rpc = (m.n + chunks - 1) / chunks;
     rpc = ((rpc + RC - 1) / RC) * RC;
     if (rpc < RC) rpc = RC;
     chunks = (int)((m.n + rpc - 1) / rpc);
     if (chunks < 1) chunks = 1;
-    const size_t need = (size_t)chunks * NP * GT * GT * sizeof(double);
-    if (need > *part_cap) {
-        cudaStreamSynchronize(d->stream);
-        cudaFree(*part_io);
-        *part_io = nullptr;
-        CUDA_TRY(cudaMalloc(part_io, need));
-        *part_cap = need;
-    }
+    double *part = nullptr;
+    CUDA_TRY(cudaMalloc(&part, (size_t)nmat * chunks * NP * GT * GT * sizeof(double)));
     const size_t smem = (size_t)RC * (Dp + 1) * sizeof(double);
-    CUDA_TRY(cudaFuncSetAttribute(gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-    gram_partial<<<dim3(chunks, gy), GRAM_THREADS, smem, d->stream>>>(m, Dz, wnode, T, NP, RC, Dp, rpc, *part_io);
-    gram_reduce<<<(NP * GT * GT + 255) / 256, 256, 0, d->stream>>>(Dz, T, NP, chunks, *part_io, dst);
+    cudaError_t e = cudaFuncSetAttribute(gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+    if (e == cudaSuccess) {
+        gram_partial<<<dim3(chunks, gy, nmat), GRAM_THREADS, smem, d->stream>>>(m, Dz, wnodes, T, NP, RC, Dp, rpc, part);
+        gram_reduce<<<dim3((NP * GT * GT + 255) / 256, nmat), 256, 0, d->stream>>>(Dz, T, NP, chunks, part, dst);
+        e = cudaStreamSynchronize(d->stream);
+    }
+    cudaFree(part);
+    CUDA_TRY(e);
+    CUDA_TRY(cudaGetLastError());
     d->timing.launches += 2;
     return ABN_OK;
 }
@@ -352,39 +358,32 @@ static int launch_gram(abn_data *d, int Dz, int wnode, double *dst, double **par
 static int compute_gram(abn_data *d, char *err, size_t errlen)
 {
     const DataMeta &m = d->m;
-    double *part = nullptr;
-    size_t part_cap = 0;
-    int rc = launch_gram(d, m.D, -1, d->dG, &part, &part_cap, err, errlen);
-    if (rc == ABN_OK) {
-        lfact_kernel<<<m.n_nodes, 256, 0, d->stream>>>(m, d->dLfact);
-        d->timing.launches += 1;
-    }
-    cudaError_t e = cudaStreamSynchronize(d->stream);
-    cudaFree(part);
+    int rc = launch_gram(d, m.D, nullptr, 1, d->dG, err, errlen);
     if (rc != ABN_OK) return rc;
-    CUDA_TRY(e);
+    lfact_kernel<<<m.n_nodes, 256, 0, d->stream>>>(m, d->dLfact);
+    d->timing.launches += 1;
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
     CUDA_TRY(cudaGetLastError());
     return ABN_OK;
 }
 
-// weighted Gram matrices of the Poisson children (start values of the mle without a data pass);
-// computed on the first mle call on a data set, never for bayes
+// weighted Gram matrices of the Poisson children (start values of the mle without a data pass):
+// one launch for all of them; computed on the first mle call on a data set, never for bayes
 static int ensure_weighted_grams(abn_data *d, char *err, size_t errlen)
 {
     if (d->gw_ready) return ABN_OK;
     const DataMeta &m = d->m;
-    double *part = nullptr;
-    size_t part_cap = 0;
-    int rc = ABN_OK;
-    for (int v = 0; rc == ABN_OK && v < m.n_nodes; v++) {
-        if (d->family[v] != ABN_POISSON) continue;
-        rc = launch_gram(d, m.D0, v, d->dGw + (size_t)d->gw_index[v] * m.D0 * m.D0, &part, &part_cap, err, errlen);
+    std::vector<int> nodes;
+    for (int v = 0; v < m.n_nodes; v++) if (d->family[v] == ABN_POISSON) nodes.push_back(v); // order = gw_index
+    if (!nodes.empty()) {
+        int *dNodes = nullptr;
+        CUDA_TRY(cudaMalloc(&dNodes, nodes.size() * sizeof(int)));
+        cudaError_t e = cudaMemcpy(dNodes, nodes.data(), nodes.size() * sizeof(int), cudaMemcpyHostToDevice);
+        int rc = (e == cudaSuccess) ? launch_gram(d, m.D0, dNodes, (int)nodes.size(), d->dGw, err, errlen) : ABN_ERR_CUDA;
+        cudaFree(dNodes);
+        CUDA_TRY(e);
+        if (rc != ABN_OK) return rc;
     }
-    cudaError_t e = cudaStreamSynchronize(d->stream);
-    cudaFree(part);
-    if (rc != ABN_OK) return rc;
-    CUDA_TRY(e);
-    CUDA_TRY(cudaGetLastError());
     d->gw_ready = true;
     return ABN_OK;
 }
