@@ -614,7 +614,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
                 else if (fam == 1) fn = get_launch_pois(k, icpt);
                 else mfn = get_launch_mn(fam, k, icpt);
                 if (mfn) {
-                    int grid = std::min((count + FIT_WARPS - 1) / FIT_WARPS, d->sm_count * 2);
+                    int grid = std::min((count + MN_WARPS - 1) / MN_WARPS, d->sm_count * 2);
                     mfn(d->m, c, d->dDescs, list, count, d->dCounters + b, rp, grid, ks);
                 } else if (!fn) {
                     n_unsupported += count;

@@ -12,11 +12,12 @@
 namespace ABN_NS {
 
 constexpr int MN_UNROLL = 2;
+constexpr int MN_WARPS = 8; // warps per CTA (its per-warp BFGS state is 5.8 KB of static shared memory)
 
 template <int L, int K, bool ICPT>
 constexpr size_t mn_stage_bytes()
 {
-    return (size_t)FIT_WARPS * FIT_STAGES * (K - (ICPT ? 1 : 0) + L - 1) * 32 * MN_UNROLL * sizeof(double);
+    return (size_t)MN_WARPS * FIT_STAGES * (K - (ICPT ? 1 : 0) + L - 1) * 32 * MN_UNROLL * sizeof(double);
 }
 
 // same cp.async staging as warp_pass_staged (fit_kernel.cuh): each lane copies and reads back only
@@ -89,12 +90,12 @@ __device__ __forceinline__ void mn_warp_pass(const double *__restrict__ y0, long
 }
 
 template <int L, int K, bool ICPT>
-__global__ void __launch_bounds__(FIT_WARPS * 32, (L - 1) * K <= 16 ? 2 : 1)
+__global__ void __launch_bounds__(MN_WARPS * 32, (L - 1) * K <= 16 ? 2 : 1)
 fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ list,
               int count, int *counter, ResultPtrs out)
 {
-    __shared__ MnState st_all[FIT_WARPS];
-    __shared__ MnAcc acc_all[FIT_WARPS];
+    __shared__ MnState st_all[MN_WARPS];
+    __shared__ MnAcc acc_all[MN_WARPS];
     __shared__ double exp_tab[ABN_EXP2_N];
     __shared__ double log_tab[128];
     if (threadIdx.x < ABN_EXP2_N) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
@@ -159,7 +160,7 @@ void launch_mn(const DataMeta &m, const Control &c, const FitDesc *descs, const 
         cudaFuncSetAttribute(fit_mn_kernel<L, K, ICPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    fit_mn_kernel<L, K, ICPT><<<grid, FIT_WARPS * 32, smem, stream>>>(m, c, descs, list, count, counter, out);
+    fit_mn_kernel<L, K, ICPT><<<grid, MN_WARPS * 32, smem, stream>>>(m, c, descs, list, count, counter, out);
 }
 
 MnLaunchFn get_launch_mn(int L, int k, int icpt); // fit_table.cu

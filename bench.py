@@ -295,8 +295,17 @@ def main():
         per_launch_bytes = top["bytes"] / top["launches"]
         per_launch_s = top["ms"] / top["launches"] / 1e3
         ach = per_launch_bytes / per_launch_s / 1e9
+        traffic, traffic_src = None, None
+        try:  # recorded ncu measurement of the same kernel (never a live number: ncu is not run inside bench.py)
+            rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top_name)
+            if rec:
+                traffic = rec["dram_bytes_per_launch"] / rec["fits_per_launch"] * (top["fits"] / top["launches"])
+                traffic_src = (f"{rec['source']}: {rec['dram_bytes_per_launch']} B for a {rec['fits_per_launch']}-fit "
+                               "launch under ncu --set full, scaled per fit to this launch size")
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "kernel": top_name, "peak_source": peak_src,
+                    "traffic": traffic, "traffic_source": traffic_src, "kernel": top_name, "peak_source": peak_src,
                     "bytes_per_launch": per_launch_bytes, "ms_per_launch": 1e3 * per_launch_s,
                     "fits_per_launch": top["fits"] / top["launches"],
                     "kernel_share_of_fit_time": top["ms"] / sum(k["ms"] for k in kernels.values()),
