@@ -3,9 +3,10 @@
 fits/s, flags and parity against the CPU oracle (full for the small real-data configs, a seeded
 random sample of candidates for the synthetic ones).
 
-    python tools/run_config.py --config 1|2|3|4|5 [--method mle|bayes] [--sample 1500] [--limit N]
+    python tests/run_config.py --config 1|2|3|4|5 [--method mle|bayes] [--sample 1500] [--limit N]
 
-Writes one JSON line (also to --out). Needs a GPU; the oracle is used only as the checker.
+Writes one JSON line (also to --out). Needs a GPU. TEST INFRASTRUCTURE (lives under tests/ because it
+loads the CPU oracle as the checker; it is not collected by pytest).
 """
 from __future__ import annotations
 
