@@ -70,13 +70,45 @@ def main():
     setup_s = time.time() - t0
     ctrl = abncache.to_c_control(abncache.build_control(method), method, d)
 
+    # one process per GPU under torchrun: every rank holds the data set, scores its interleaved share
+    # of the candidate list, and the score vectors are all-gathered over NCCL (abn_b200/shard.py)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        from abn_b200 import shard
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        ctrl.device = local_rank
+        idx = shard.partition(len(ch0), world, rank, block=1024)
+    else:
+        idx = np.arange(len(ch0))
     t1 = time.time()
-    with abncache.DeviceData(P, device=0) as dev:
+    with abncache.DeviceData(P, device=local_rank) as dev:
         create_s = time.time() - t1
+        if world > 1:
+            dist.barrier()
         t2 = time.time()
-        res = dev.score(ch0, par, ctrl)
-        score_s = time.time() - t2
+        res = dev.score(ch0[idx], par[idx], ctrl)
+        score_local_s = time.time() - t2
         timing = dev.timing()
+    gather_s = 0.0
+    if world > 1:
+        tt = torch.tensor([score_local_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        score_s = float(tt.item())
+        t4 = time.time()
+        res = shard.gather({k: res[k] for k in ("mlik", "aic", "bic", "mdl", "status", "iters")}, len(ch0), world, rank,
+                           block=1024, device=f"cuda:{local_rank}")
+        torch.cuda.synchronize()
+        gather_s = time.time() - t4
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
+            return
+    else:
+        score_s = score_local_s
     fits = len(ch0)
     fam = P.node_family[ch0]
 
@@ -108,6 +140,7 @@ def main():
     line = {
         "config": args.config, "method": method, "n": int(P.n), "d": d, "max_parents": int(mp),
         "candidates_total": int(rows_total), "candidates_scored": int(fits),
+        "n_gpus": world, "allgather_s": gather_s,
         "setup_s": setup_s, "data_create_s": create_s, "score_s": score_s,
         "fits_per_s": fits / score_s, "fits_per_s_incl_upload": fits / (score_s + create_s),
         "device_ms": {k: timing[k] for k in ("h2d_ms", "plan_ms", "fit_ms", "d2h_ms")},
@@ -124,6 +157,8 @@ def main():
     if args.out:
         with open(args.out, "w") as f:
             f.write(s + "\n")
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
