@@ -3,7 +3,7 @@
 // The fit kernels are bound by instruction issue and the FP64 pipe, not by HBM (ncu: profiles/):
 // libdevice's exp() / log() / IEEE division cost ~35 / ~45 / ~25 instructions each including
 // range branches and slow paths that these loops never need. The versions here cost
-//   exp    9 FP64 + 5 integer/LDS instructions   (max error 1.25 ulp, mean 0.34 ulp on |t| <= 700:
+//   exp    9 FP64 + 5 integer/LDS instructions   (max error 1.32 ulp, mean 0.34 ulp on |t| <= 700:
 //                                                 tests/test_fastmath.py against long double)
 //   rcp    1 MUFU + 5 FP64                        (correctly rounded 1/d for normal d: Markstein)
 // __host__ __device__ with identical arithmetic (FMA on both sides) so tests/host_sim.cpp
@@ -66,30 +66,57 @@ ABN_HD uint64_t double_to_bits(double d)
 #endif
 }
 
+// high 32 bits of a double (sign, exponent, top 20 mantissa bits) and a double with them replaced.
+// The row ops do their range checks and clamps on this word with integer min / max: one ALU
+// instruction each, where fmax() / a double compare costs an FP64-pipe DSETP plus selects.
+ABN_HD int hi_word(double d)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(d);
+#else
+    return (int)(uint32_t)(double_to_bits(d) >> 32);
+#endif
+}
+
+ABN_HD double with_hi_word(double d, int hi)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, __double2loint(d));
+#else
+    return bits_to_double(((uint64_t)(uint32_t)hi << 32) | (double_to_bits(d) & 0xffffffffull));
+#endif
+}
+
 // exp(t) for |t| <= 700 (callers clamp). `tab` points at the 64-entry table: shared memory on the
 // device (lane-dependent index: a __constant__ read would serialise), h_exp2_table on the host.
 //   t = (64 k + j) ln2/64 + r,  |r| <= ln2/128;  exp(t) = 2^k * 2^(j/64) * (1 + p(r))
 ABN_HD double fast_exp(double t, const double *tab)
 {
+    // Constants whose low 32 bits are zero are encoded as immediates of the FP64 instructions;
+    // the others cost two register moves per use site. So: INV only steers the choice of n (any
+    // n within +-0.03 of the ideal keeps |r| < 0.0056), LN2_64_HI is ln2/64 cut to its high word
+    // (n * HI exact for |n| < 2^32), and the r^4 / r^5 coefficients are rounded to 21 bits
+    // (error < 1e-8 * r^4 < 1e-17).
     const double MAGIC = 6755399441055744.0;        // 1.5 * 2^52: round-to-nearest-integer trick
-    const double INV = 92.33248261689366;           // 64 / ln 2
-    const double LN2_64_HI = 0.01083042468962958;   // ln2/64, low 22 mantissa bits zero: n * HI exact
-    const double LN2_64_LO = 6.619564634077006e-12;
+    const double INV = 92.33245849609375;           // 64 / ln 2 to 21 bits (0x40571547 00000000)
+    const double LN2_64_HI = 0.010830417275428772;  // 0x3f862e42 00000000
+    const double LN2_64_LO = 7.420820373486988e-09; // ln2/64 - HI
+    const double C4 = 0.041666656732559204;         // 1/24  (0x3fa55555 00000000)
+    const double C5 = 0.00833333283662796;          // 1/120 (0x3f811111 00000000)
     const double kd = fma(t, INV, MAGIC);
     const double nf = kd - MAGIC;                   // n = 64 k + j as a double
-    double r = fma(nf, -LN2_64_HI, t);
+    double r = fma(nf, -LN2_64_HI, t);              // exact
     r = fma(nf, -LN2_64_LO, r);
-    const int64_t n = (int64_t)(int32_t)(uint32_t)double_to_bits(kd); // low word of kd holds n
-    const int j = (int)(n & 63);
-    const int64_t k = n >> 6;
-    // p(r) = r + r^2/2 + r^3/6 + r^4/24 + r^5/120, |r| <= 0.00542: truncation < 4e-17
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    const int n = (int)(uint32_t)double_to_bits(kd); // low word of kd holds n
+    // p(r) = r + r^2/2 + r^3/6 + r^4/24 + r^5/120, |r| <= 0.0056: truncation < 5e-17
+    double p = fma(r, C5, C4);
     p = fma(p, r, 1.0 / 6.0);
     p = fma(p, r, 0.5);
     p = fma(p * r, r, r);
-    const double tj = tab[j];
-    const double v = fma(tj, p, tj);                // in [1, 2) * (1 +- 0.0055)
-    return bits_to_double(double_to_bits(v) + ((uint64_t)k << 52)); // * 2^k, k in [-1010, 1010]
+    const double tj = tab[n & 63];
+    const double v = fma(tj, p, tj);                // in [1, 2) * (1 +- 0.0056)
+    // * 2^k, k = n >> 6 in [-1010, 1010]: add k to the exponent field, i.e. (n >> 6) << 20 to the high word
+    return with_hi_word(v, hi_word(v) + (int)(((uint32_t)n << 14) & 0xfff00000u));
 }
 
 // 1 / d, correctly rounded for normal d with a normal result. MUFU.RCP64H seeds ~2^-20; one step

@@ -45,7 +45,7 @@ __device__ __forceinline__ double warp_sum(double v)
 // contribution of one row to the register accumulators
 template <int KIND, int K, bool ICPT, bool NEED_H, bool NEED_G, bool NEED_L, bool VOTE = false>
 __device__ __forceinline__ void row_update(const double (&xd)[K], double yi, const double (&beta)[K], const RowConst &rc,
-                                           double (&H)[K * (K + 1) / 2], double (&g)[K], double &ll, int &bad)
+                                           double (&H)[K * (K + 1) / 2], double (&g)[K], double &ll, RowTrack &bad)
 {
     // xd[j] holds design column j; with ICPT column 0 is the constant 1 and xd[0] is unused
     double eta = ICPT ? beta[0] : 0.0;
@@ -100,7 +100,7 @@ __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const do
     double H[K * (K + 1) / 2];
     double g[K];
     double ll = 0.0;
-    int bad = 0;
+    RowTrack tk = row_track_init();
 #pragma unroll
     for (int j = 0; j < K * (K + 1) / 2; j++) H[j] = 0.0;
 #pragma unroll
@@ -136,13 +136,13 @@ __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const do
         }
 #pragma unroll
         for (int u = 0; u < U; u++)
-            row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L, true>(xc[u], yc[u], beta, rc, H, g, ll, bad);
+            row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L, true>(xc[u], yc[u], beta, rc, H, g, ll, tk);
     }
     for (long long i = n_main + lane; i < n; i += 32) { // tail: fewer than 32 * U rows
         double xt[K];
 #pragma unroll
         for (int j = 0; j < KD; j++) xt[j + I0] = __ldg(cp[j] + i);
-        row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L>(xt, __ldg(y + i), beta, rc, H, g, ll, bad);
+        row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L>(xt, __ldg(y + i), beta, rc, H, g, ll, tk);
     }
 
     // fixed-order butterfly: every lane ends with the same totals
@@ -155,7 +155,7 @@ __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const do
         for (int j = 0; j < K; j++) g[j] = warp_sum(g[j]);
     }
     if (NEED_L) ll = warp_sum(ll);
-    bad = __any_sync(0xffffffffu, bad);
+    const int bad = __any_sync(0xffffffffu, RowOp<KIND>::bad_of(tk));
     if (lane == 0) {
         if (NEED_H) {
 #pragma unroll
@@ -171,6 +171,9 @@ __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const do
 }
 
 
+#ifndef ABN_BIN_NOY
+#define ABN_BIN_NOY 1 // binomial passes that do not stream the response (warp_pass_bin)
+#endif
 #ifndef ABN_STAGE
 #define ABN_STAGE 1   // 1: stage the column tiles through shared memory with cp.async; 0: register double buffering
 #endif
@@ -218,38 +221,47 @@ __device__ __forceinline__ void warp_pass_staged(const double *__restrict__ y, c
     double H[K * (K + 1) / 2];
     double g[K];
     double ll = 0.0;
-    int bad = 0;
+    RowTrack tk = row_track_init();
 #pragma unroll
     for (int j = 0; j < K * (K + 1) / 2; j++) H[j] = 0.0;
 #pragma unroll
     for (int j = 0; j < K; j++) g[j] = 0.0;
 
-    const long long n_main = (n / TROWS) * TROWS;
-    // tile layout: [stage][column][row in tile]; lane touches rows lane + 32 u only
-    auto issue = [&](long long base, int stage) {
-        double *t = tile + (size_t)stage * NC * TROWS;
+    const int ntiles = (int)(n / TROWS);
+    const long long n_main = (long long)ntiles * TROWS;
+    // tile layout: [stage][column][row in tile]; lane touches rows lane + 32 u only. The source
+    // pointers advance by one tile per issue (no per-tile address arithmetic beyond K adds).
+    const double *pc[KD > 0 ? KD : 1];
+#pragma unroll
+    for (int j = 0; j < KD; j++) pc[j] = cp[j] + lane;
+    const double *py = y + lane;
+    double *const tlane = tile + lane;
+    auto issue = [&](int stage) {
+        double *t = tlane + stage * (NC * TROWS);
 #pragma unroll
         for (int u = 0; u < U; u++) {
 #pragma unroll
-            for (int j = 0; j < KD; j++) cp_async8(t + j * TROWS + u * 32 + lane, cp[j] + base + u * 32 + lane);
-            cp_async8(t + KD * TROWS + u * 32 + lane, y + base + u * 32 + lane);
+            for (int j = 0; j < KD; j++) cp_async8(t + j * TROWS + u * 32, pc[j] + u * 32);
+            cp_async8(t + KD * TROWS + u * 32, py + u * 32);
         }
         cp_async_commit();
+#pragma unroll
+        for (int j = 0; j < KD; j++) pc[j] += TROWS;
+        py += TROWS;
     };
-    if (n_main > 0) issue(0, 0);
+    if (ntiles > 0) issue(0);
     int stage = 0;
-    for (long long base = 0; base < n_main; base += TROWS) {
-        const long long nb = base + TROWS;
-        if (nb < n_main) { issue(nb, stage ^ 1); cp_async_wait<1>(); }
+    for (int it = 0; it < ntiles; it++) {
+        if (it + 1 < ntiles) { issue(stage ^ 1); cp_async_wait<1>(); }
         else cp_async_wait<0>();
-        const double *t = tile + (size_t)stage * NC * TROWS;
+        const double *t = tlane + stage * (NC * TROWS);
 #pragma unroll
         for (int u = 0; u < U; u++) {
             double xr[K];
 #pragma unroll
-            for (int j = 0; j < KD; j++) xr[j + I0] = t[j * TROWS + u * 32 + lane];
-            const double yi = t[KD * TROWS + u * 32 + lane];
-            row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L, true>(xr, yi, beta, rc, H, g, ll, bad);
+            for (int j = 0; j < KD; j++) xr[j + I0] = t[j * TROWS + u * 32];
+            const double yi = t[KD * TROWS + u * 32];
+            row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L, true>(xr, yi, beta, rc, H, g, ll, tk);
         }
         stage ^= 1;
     }
@@ -257,7 +269,7 @@ __device__ __forceinline__ void warp_pass_staged(const double *__restrict__ y, c
         double xt[K];
 #pragma unroll
         for (int j = 0; j < KD; j++) xt[j + I0] = __ldg(cp[j] + i);
-        row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L>(xt, __ldg(y + i), beta, rc, H, g, ll, bad);
+        row_update<KIND, K, ICPT, NEED_H, NEED_G, NEED_L>(xt, __ldg(y + i), beta, rc, H, g, ll, tk);
     }
 
     if (NEED_H) {
@@ -269,7 +281,7 @@ __device__ __forceinline__ void warp_pass_staged(const double *__restrict__ y, c
         for (int j = 0; j < K; j++) g[j] = warp_sum(g[j]);
     }
     if (NEED_L) ll = warp_sum(ll);
-    bad = __any_sync(0xffffffffu, bad);
+    const int bad = __any_sync(0xffffffffu, RowOp<KIND>::bad_of(tk));
     if (lane == 0) {
         if (NEED_H) {
 #pragma unroll
@@ -284,12 +296,300 @@ __device__ __forceinline__ void warp_pass_staged(const double *__restrict__ y, c
     }
 }
 
+
+// Poisson with an intercept: the score and the log-likelihood need no sums of their own.
+//   w = E = exp(eta), r = y - E  =>  g_j = (X'y)_j - sum E x_j = (X'y)_j - H_0j   (column 0 is the intercept)
+//   ll = sum (y eta - E) = beta'(X'y) - H_00                                       (lfact is subtracted later)
+// and X'y is a column of the global Gram matrix. So the pass streams only the design columns (not
+// the response), evaluates one exp per row, and accumulates H - all of it (FULL / HG / HESS), its
+// first row (GRAD) or H_00 alone (LL). `xty` holds (X'y)_j for this fit.
+template <int K, int MODE>
+__device__ __forceinline__ void warp_pass_pois(const double *const (&cp)[MAXK], const double *beta_sm, const double *xty,
+                                               long long n, const RowConst rc, PassAcc *acc_sm, double *tile)
+{
+    constexpr int KD = K - 1;
+    constexpr int U = FIT_UNROLL;
+    constexpr int TROWS = 32 * U;
+    constexpr bool ALL_H = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_HESS);
+    constexpr int NH = ALL_H ? K * (K + 1) / 2 : (MODE == PASS_GRAD ? K : 1);
+    const int lane = threadIdx.x & 31;
+
+    double beta[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) beta[j] = beta_sm[j];
+    double H[NH];
+#pragma unroll
+    for (int j = 0; j < NH; j++) H[j] = 0.0;
+    RowTrack tk = row_track_init();
+
+    auto row = [&](const double (&x)[K]) { // x[0] unused (intercept)
+        double eta = beta[0];
+#pragma unroll
+        for (int j = 1; j < K; j++) eta = fma(x[j], beta[j], eta);
+        row_track(tk, eta);
+        const double E = fast_exp(clamp_lo700(eta), rc.tab);
+        H[0] += E;
+        if (ALL_H) {
+            int t = 1;
+#pragma unroll
+            for (int q = 1; q < K; q++) { H[t] = fma(E, x[q], H[t]); t++; }
+#pragma unroll
+            for (int p = 1; p < K; p++) {
+                const double wx = E * x[p];
+#pragma unroll
+                for (int q = p; q < K; q++) { H[t] = fma(wx, x[q], H[t]); t++; }
+            }
+        } else if (MODE == PASS_GRAD) {
+#pragma unroll
+            for (int q = 1; q < K; q++) H[q] = fma(E, x[q], H[q]);
+        }
+    };
+
+    constexpr int NCP = KD > 0 ? KD : 1;
+    const int ntiles = (KD > 0) ? (int)(n / TROWS) : 0;
+    const long long n_main = (long long)ntiles * TROWS;
+    const double *pc[NCP];
+#pragma unroll
+    for (int j = 0; j < KD; j++) pc[j] = cp[j] + lane;
+    double *const tlane = tile + lane;
+    auto issue = [&](int stage) {
+        double *t = tlane + stage * (NCP * TROWS);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int j = 0; j < KD; j++) cp_async8(t + j * TROWS + u * 32, pc[j] + u * 32);
+        cp_async_commit();
+#pragma unroll
+        for (int j = 0; j < KD; j++) pc[j] += TROWS;
+    };
+    if (ntiles > 0) issue(0);
+    int stage = 0;
+    for (int it = 0; it < ntiles; it++) {
+        if (it + 1 < ntiles) { issue(stage ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        const double *t = tlane + stage * (NCP * TROWS);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            double xr[K];
+#pragma unroll
+            for (int j = 0; j < KD; j++) xr[j + 1] = t[j * TROWS + u * 32];
+            row(xr);
+        }
+        stage ^= 1;
+    }
+    for (long long i = n_main + lane; i < n; i += 32) {
+        double xt[K];
+#pragma unroll
+        for (int j = 0; j < KD; j++) xt[j + 1] = __ldg(cp[j] + i);
+        row(xt);
+    }
+#pragma unroll
+    for (int j = 0; j < NH; j++) H[j] = warp_sum(H[j]);
+    const int bad = __any_sync(0xffffffffu, RowOp<RK_POIS>::bad_of(tk));
+    if (lane == 0) {
+        if (ALL_H) {
+#pragma unroll
+            for (int j = 0; j < K * (K + 1) / 2; j++) acc_sm->H[j] = H[j];
+        }
+        if (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_GRAD) {
+            // H row 0 is H[0..K-1] in both layouts (packed upper triangle starts with row 0)
+#pragma unroll
+            for (int j = 0; j < K; j++) acc_sm->g[j] = xty[j] - H[j];
+        }
+        if (MODE == PASS_FULL || MODE == PASS_LL) {
+            double s = -H[0];
+#pragma unroll
+            for (int j = 0; j < K; j++) s = fma(beta[j], xty[j], s);
+            acc_sm->ll = s;
+        } else {
+            acc_sm->ll = 0.0;
+        }
+        acc_sm->bad = bad;
+    }
+}
+
+
+// Binomial child with an intercept: the response column is not streamed either.
+//   mle   r_i = rho_i (b'_i - g_i), b'_i = bp0 + y_i (bp1 - bp0), l_i = -log(1 + e_i) - (1 - y_i) eta_i
+//         X'r = bp0 X'1 + (bp1 - bp0) X'y - S,   S_j = sum_i gv_i x_ij,   gv = g - (rho - 1)(b' - g)
+//         ll  = beta'(X'y) - beta'(X'1) - sum_i log(1 + e_i)
+//   bayes r_i = y_i - sigma_i, l_i = y_i eta_i - log(1 + E_i)   (eta_i for eta_i >= 700)
+//         X'r = X'y - S,  S_j = sum_i sigma_i x_ij;   ll = beta'(X'y) - sum_i log(1 + E_i)
+// with X'y and X'1 columns of the global Gram matrix (`xty`, `xt1`). The mle rho correction (see
+// RowOp<RK_BIN_MLE>) is taken only in warp steps where some row has eta >= BIN_RHO_ETA; those
+// steps fetch y straight from global memory, form g with the correctly rounded reciprocal and
+// W = rho g' exactly as the row op does. Elsewhere rho = 1 to 2e-11, g comes from the cubic
+// reciprocal step and g' = g - g^2 (equal to e g^2 to 1e-16 / (1 - g) <= 2e-11 relative; g'
+// only weights the Hessian of the IRLS step, never the fixed point).
+template <int KIND, int K, int MODE>
+__device__ __forceinline__ void warp_pass_bin(const double *__restrict__ y, const double *const (&cp)[MAXK],
+                                              const double *beta_sm, const double *xty, const double *xt1, long long n,
+                                              const RowConst rc, PassAcc *acc_sm, double *tile)
+{
+    constexpr int KD = K - 1;
+    constexpr int U = FIT_UNROLL;
+    constexpr int TROWS = 32 * U;
+    constexpr bool NEED_H = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_HESS);
+    constexpr bool NEED_G = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_GRAD);
+    constexpr bool NEED_L = (MODE == PASS_FULL || MODE == PASS_LL);
+    constexpr bool MLE_ = (KIND == RK_BIN_MLE);
+    const int lane = threadIdx.x & 31;
+
+    double beta[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) beta[j] = beta_sm[j];
+    double H[K * (K + 1) / 2];
+    double S[K];
+    double L = 0.0;
+#pragma unroll
+    for (int j = 0; j < K * (K + 1) / 2; j++) H[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; j++) S[j] = 0.0;
+    RowTrack tk = row_track_init();
+    const double dbp = rc.bp1 - rc.bp0;
+
+    // x[0] unused (intercept); yp points at this row's response, read only on the rho path
+    auto row = [&](const double (&x)[K], const double *yp, bool vote) {
+        double eta = beta[0];
+#pragma unroll
+        for (int j = 1; j < K; j++) eta = fma(x[j], beta[j], eta);
+        double w = 0.0, gv = 0.0;
+        if (MLE_) {
+            row_track(tk, eta);
+            const double e = fast_exp(-eta, rc.tab);
+            const double d = 1.0 + e;
+            if (NEED_H || NEED_G) {
+                const bool need_rho = vote ? __any_sync(0xffffffffu, eta >= BIN_RHO_ETA) : true;
+                if (need_rho) {
+                    const double g = fast_rcp(d);
+                    const double gp = e * g * g;
+                    const double rho = gp * fast_rcp_approx(g * (1.0 - g));
+                    const double bpg = fma(__ldg(yp), dbp, rc.bp0) - g;
+                    w = rho * gp;
+                    gv = fma(-(rho - 1.0), bpg, g);
+                } else {
+                    const double g = fast_rcp_approx(d);
+                    w = fma(-g, g, g);
+                    gv = g;
+                }
+            }
+            if (NEED_L) L += fast_log_ge1(d, rc.logtab);
+        } else {
+            const double E = fast_exp(clamp700(eta), rc.tab);
+            const double d = 1.0 + E;
+            if (NEED_H || NEED_G) {
+                const double inv = fast_rcp_approx(d);
+                gv = E * inv;
+                w = gv * inv;
+            }
+            if (NEED_L) L += (hi_word(eta) >= 0x4085E000) ? eta : fast_log_ge1(d, rc.logtab);
+        }
+        if (NEED_H) {
+            H[0] += w;
+            int t = 1;
+#pragma unroll
+            for (int q = 1; q < K; q++) { H[t] = fma(w, x[q], H[t]); t++; }
+#pragma unroll
+            for (int p = 1; p < K; p++) {
+                const double wx = w * x[p];
+#pragma unroll
+                for (int q = p; q < K; q++) { H[t] = fma(wx, x[q], H[t]); t++; }
+            }
+        }
+        if (NEED_G) {
+            S[0] += gv;
+#pragma unroll
+            for (int q = 1; q < K; q++) S[q] = fma(gv, x[q], S[q]);
+        }
+    };
+
+    constexpr int NCP = KD > 0 ? KD : 1;
+    const int ntiles = (KD > 0) ? (int)(n / TROWS) : 0;
+    const long long n_main = (long long)ntiles * TROWS;
+    const double *pc[NCP];
+#pragma unroll
+    for (int j = 0; j < KD; j++) pc[j] = cp[j] + lane;
+    double *const tlane = tile + lane;
+    auto issue = [&](int stage) {
+        double *t = tlane + stage * (NCP * TROWS);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int j = 0; j < KD; j++) cp_async8(t + j * TROWS + u * 32, pc[j] + u * 32);
+        cp_async_commit();
+#pragma unroll
+        for (int j = 0; j < KD; j++) pc[j] += TROWS;
+    };
+    if (ntiles > 0) issue(0);
+    int stage = 0;
+    const double *yrow = y + lane;
+    for (int it = 0; it < ntiles; it++) {
+        if (it + 1 < ntiles) { issue(stage ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        const double *t = tlane + stage * (NCP * TROWS);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            double xr[K];
+#pragma unroll
+            for (int j = 0; j < KD; j++) xr[j + 1] = t[j * TROWS + u * 32];
+            row(xr, yrow + u * 32, true);
+        }
+        yrow += TROWS;
+        stage ^= 1;
+    }
+    for (long long i = n_main + lane; i < n; i += 32) {
+        double xt[K];
+#pragma unroll
+        for (int j = 0; j < KD; j++) xt[j + 1] = __ldg(cp[j] + i);
+        row(xt, y + i, false);
+    }
+    if (NEED_H) {
+#pragma unroll
+        for (int j = 0; j < K * (K + 1) / 2; j++) H[j] = warp_sum(H[j]);
+    }
+    if (NEED_G) {
+#pragma unroll
+        for (int j = 0; j < K; j++) S[j] = warp_sum(S[j]);
+    }
+    if (NEED_L) L = warp_sum(L);
+    const int bad = __any_sync(0xffffffffu, RowOp<KIND>::bad_of(tk));
+    if (lane == 0) {
+        if (NEED_H) {
+#pragma unroll
+            for (int j = 0; j < K * (K + 1) / 2; j++) acc_sm->H[j] = H[j];
+        }
+        if (NEED_G) {
+#pragma unroll
+            for (int j = 0; j < K; j++)
+                acc_sm->g[j] = MLE_ ? fma(dbp, xty[j], rc.bp0 * xt1[j]) - S[j] : xty[j] - S[j];
+        }
+        double ll = 0.0;
+        if (NEED_L) {
+            ll = -L;
+#pragma unroll
+            for (int j = 0; j < K; j++) ll = fma(beta[j], MLE_ ? xty[j] - xt1[j] : xty[j], ll);
+        }
+        acc_sm->ll = ll;
+        acc_sm->bad = bad;
+    }
+}
+
 template <int KIND, int K, bool ICPT, int MODE>
 __device__ __forceinline__ void run_pass(const double *__restrict__ y, const double *const (&cp)[MAXK],
                                          const double *beta_sm, long long n, const RowConst rc, PassAcc *acc_sm,
-                                         double *tile)
+                                         double *tile, const double *xty)
 {
 #if ABN_STAGE
+    if (KIND == RK_POIS && ICPT) {
+        warp_pass_pois<K, MODE>(cp, beta_sm, xty, n, rc, acc_sm, tile);
+        return;
+    }
+#if ABN_BIN_NOY
+    if ((KIND == RK_BIN_MLE || KIND == RK_BIN_BAYES) && ICPT) {
+        warp_pass_bin<KIND == RK_BIN_MLE ? RK_BIN_MLE : RK_BIN_BAYES, K, MODE>(y, cp, beta_sm, xty, xty + MAXK, n, rc, acc_sm, tile);
+        return;
+    }
+#endif
     warp_pass_staged<KIND, K, ICPT, MODE>(y, cp, beta_sm, n, rc, acc_sm, tile);
 #else
     warp_pass<KIND, K, ICPT, MODE>(y, cp, beta_sm, n, rc, acc_sm);
@@ -304,6 +604,7 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
 {
     __shared__ FitState st_all[FIT_WARPS];
     __shared__ PassAcc acc_all[FIT_WARPS];
+    __shared__ double xty_all[FIT_WARPS][2 * MAXK]; // (X'y)_j and (X'1)_j of the fit in flight (passes without y)
     __shared__ double exp_tab[ABN_EXP2_N];
     __shared__ double lnmu_tab[64];
     __shared__ double log_tab[128];
@@ -316,6 +617,7 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
     FitState &st = st_all[warp];
     PassAcc *acc = &acc_all[warp];
     double *tile = stage_tiles + (size_t)warp * FIT_STAGES * (K - (ICPT ? 1 : 0) + 1) * 32 * FIT_UNROLL;
+    double *xty = xty_all[warp];
 
     for (;;) {
         int idx = 0;
@@ -338,6 +640,13 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
 
         int mode = 0;
         if (lane == 0) {
+            if (KIND != RK_PINIT) {
+                const long long gy = gram_col(d.ycol);
+                for (int j = 0; j < K; j++) {
+                    xty[j] = m.G[(long long)gidx(d, j) * m.D + gy];
+                    xty[MAXK + j] = m.G[(long long)gidx(d, j) * m.D];
+                }
+            }
             state_setup(m, d, ch, c, st);
             if (c.method == BAYES) bayes_inits(m, d, ch, st);
             mode = fit_begin(st, c);
@@ -357,12 +666,12 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
         __syncwarp();
         while (mode != PASS_DONE) {
             // only the modes a row kind's state machines can ask for are instantiated
-            if (mode == PASS_HG) run_pass<KIND, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile);
-            else if (mode == PASS_FULL) run_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc, tile);
-            else if (mode == PASS_LL) run_pass<KIND, K, ICPT, PASS_LL>(y, cp, st.x, m.n, rc, acc, tile);
-            else if (KIND != RK_BIN_MLE && mode == PASS_GRAD) run_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc, tile);
-            else if (KIND != RK_BIN_MLE && mode == PASS_HESS) run_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc, tile);
-            else if (KIND == RK_POIS && mode == PASS_PINIT) run_pass<RK_PINIT, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile);
+            if (mode == PASS_HG) run_pass<KIND, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty);
+            else if (mode == PASS_FULL) run_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc, tile, xty);
+            else if (mode == PASS_LL) run_pass<KIND, K, ICPT, PASS_LL>(y, cp, st.x, m.n, rc, acc, tile, xty);
+            else if (KIND != RK_BIN_MLE && mode == PASS_GRAD) run_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc, tile, xty);
+            else if (KIND != RK_BIN_MLE && mode == PASS_HESS) run_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc, tile, xty);
+            else if (KIND == RK_POIS && mode == PASS_PINIT) run_pass<RK_PINIT, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty);
             __syncwarp();
             if (lane == 0) mode = fit_consume(st, c, *acc);
             mode = __shfl_sync(0xffffffffu, mode, 0);

@@ -42,7 +42,50 @@ ABN_HD RowConst make_row_const(int k, double n, const double *tab, const double 
 
 constexpr double BIN_RHO_ETA = 12.0;
 
-ABN_HD double clamp700(double t) { return fmin(fmax(t, -700.0), 700.0); }
+// Range bookkeeping of one data pass, kept on the HIGH WORD of eta with integer max (fastmath.cuh):
+//   smax  signed max   - positive doubles order like their high words, negatives sort below them
+//   umax  unsigned max - negative doubles (sign bit set) sort above every positive, by magnitude
+// so "some eta >= a" is smax >= hi(a) for a > 0 and "some eta <= -b" is umax >= hi(-b); NaNs of
+// either sign exceed every finite bound on one of the two. The bounds are compared on the high
+// word only: a fit is flagged when eta comes within 2^-20 relative of the exact limit (the limits
+// are where the reference's arithmetic overflows; nothing meaningful lives that close to them).
+struct RowTrack {
+    int smax;
+    unsigned umax;
+    int flag;
+};
+
+ABN_HD RowTrack row_track_init()
+{
+    RowTrack t;
+    t.smax = (int)0x80000000u;
+    t.umax = 0u;
+    t.flag = 0;
+    return t;
+}
+
+ABN_HD void row_track(RowTrack &t, double eta)
+{
+    const int h = hi_word(eta);
+    t.smax = t.smax > h ? t.smax : h;
+    t.umax = t.umax > (unsigned)h ? t.umax : (unsigned)h;
+}
+
+// eta clamped to [-700.0005, 700.0005] (the low word is kept: the bound moves by < 2^-11), NaN -> +-700
+ABN_HD double clamp700(double t)
+{
+    const unsigned h = (unsigned)hi_word(t);
+    unsigned a = h & 0x7fffffffu;
+    a = a < 0x4085E000u ? a : 0x4085E000u; // hi(700.0)
+    return with_hi_word(t, (int)(a | (h & 0x80000000u)));
+}
+
+// eta clamped from below only, same convention; positive values (and +NaN) pass through
+ABN_HD double clamp_lo700(double t)
+{
+    const unsigned h = (unsigned)hi_word(t);
+    return with_hi_word(t, (int)(h < 0xC085E000u ? h : 0xC085E000u)); // hi(-700.0)
+}
 
 template <int KIND>
 struct RowOp;
@@ -65,13 +108,13 @@ struct RowOp<RK_BIN_MLE> {
     // three orders under the IRLS stop tolerance, and the score by ~1e-20 - while the saturated
     // rows, where the reference's noise is visible at 1e-8, always take the exact path.
     template <bool NEED_W, bool NEED_R, bool NEED_L>
-    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad, bool need_rho = true)
+    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, RowTrack &tk, bool need_rho = true)
     {
         // The reference's W or z is non-finite when g rounds to 1 (g(1-g) = 0: 1 + e == 1, i.e.
         // eta >= 53 ln 2) or when (1+e)^2 overflows (e >= sqrt(DBL_MAX), eta <= -354.89). Outside
         // that window the fit is flagged and whatever fast_exp returns is never used; inside it
         // fast_exp needs no range clamp.
-        bad |= !((eta < 36.7368005696771) & (eta > -354.891356446692));
+        row_track(tk, eta);
         const double e = fast_exp(-eta, c.tab);
         const double d = 1.0 + e;
         if (NEED_W || NEED_R) {
@@ -89,19 +132,23 @@ struct RowOp<RK_BIN_MLE> {
         }
         if (NEED_L) l = -fast_log_ge1(d, c.logtab) - (1.0 - y) * eta;
     }
+    // eta >= 53 ln 2 = 36.7368005696771 (0x40425E4F 7B2737FA) or eta <= -354.891356446692 (0xC0762E42 ...)
+    static ABN_HD int bad_of(const RowTrack &tk) { return (tk.smax >= 0x40425E4F) | (tk.umax >= 0xC0762E42u) | tk.flag; }
 };
 
 template <>
 struct RowOp<RK_POIS> {
     template <bool NEED_W, bool NEED_R, bool NEED_L>
-    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad, bool need_rho = true)
+    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, RowTrack &tk, bool need_rho = true)
     {
-        bad |= !(eta < 709.782712893384); // exp(eta) = +Inf (or eta is NaN) in the reference
-        const double E = fast_exp(fmax(eta, -700.0), c.tab); // flagged fits never use E; no upper clamp
+        row_track(tk, eta);
+        const double E = fast_exp(clamp_lo700(eta), c.tab); // flagged fits never use E; no upper clamp
         w = E;
         r = y - E;
         if (NEED_L) l = fma(y, eta, -E);
     }
+    // exp(eta) = +Inf in the reference from eta >= 709.782712893384 (0x40862E42 FEFA39EF); NaN either sign
+    static ABN_HD int bad_of(const RowTrack &tk) { return (tk.smax >= 0x40862E42) | (tk.umax > 0xFFF00000u) | tk.flag; }
 };
 
 template <>
@@ -110,7 +157,7 @@ struct RowOp<RK_BIN_BAYES> {
     // hessian weight exp(eta - 2 log(1+E)) = sigma/(1+E) (:761-764), log term log(1+E) (eta if E
     // overflows, :633-639). For |eta| > 700 the clamped E gives the same doubles as those branches.
     template <bool NEED_W, bool NEED_R, bool NEED_L>
-    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, int &bad, bool need_rho = true)
+    static ABN_HD void apply(double eta, double y, const RowConst &c, double &w, double &r, double &l, RowTrack &tk, bool need_rho = true)
     {
         const double E = fast_exp(clamp700(eta), c.tab);
         const double d = 1.0 + E;
@@ -120,10 +167,11 @@ struct RowOp<RK_BIN_BAYES> {
             w = sig * inv;
             r = y - sig;
         }
-        if (NEED_L) l = (eta > 700.0) ? (y * eta - eta) : (y * eta - fast_log_ge1(d, c.logtab));
-        (void)bad;
+        if (NEED_L) l = (hi_word(eta) >= 0x4085E000) ? (y * eta - eta) : (y * eta - fast_log_ge1(d, c.logtab)); // eta >= 700
+        (void)tk;
         (void)need_rho;
     }
+    static ABN_HD int bad_of(const RowTrack &tk) { return tk.flag; }
 };
 
 template <>
@@ -132,7 +180,7 @@ struct RowOp<RK_PINIT> {
     // H = X'W0X, g = X'W0z0 with W0 z0 = W0 eta0 + (y - W0): no division needed. Counts are small
     // integers, so log(y + 0.1) comes from a 64-entry table; other values take the libm path.
     template <bool NEED_W, bool NEED_R, bool NEED_L>
-    static ABN_HD void apply(double, double y, const RowConst &c, double &w, double &r, double &l, int &bad, bool need_rho = true)
+    static ABN_HD void apply(double, double y, const RowConst &c, double &w, double &r, double &l, RowTrack &tk, bool need_rho = true)
     {
         const double mu = y + 0.1;
         const int yi = (int)y;
@@ -141,9 +189,10 @@ struct RowOp<RK_PINIT> {
         else eta0 = log(mu);
         w = mu;
         r = fma(mu, eta0, y - mu);
-        bad |= !(mu > 0.0) | !(mu < 1.79769313486231570815e308);
+        tk.flag |= !(mu > 0.0) | !(mu < 1.79769313486231570815e308);
         if (NEED_L) l = 0.0;
     }
+    static ABN_HD int bad_of(const RowTrack &tk) { return tk.flag; }
 };
 
 } // namespace ABN_NS

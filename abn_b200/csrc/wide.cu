@@ -60,7 +60,7 @@ __device__ void wide_pass(const DataMeta &m, const Control &c, WideShared &S, in
 #pragma unroll
     for (int t = 0; t < PPL; t++) hacc[t] = 0.0;
     double gacc = 0.0, ll = 0.0;
-    int bad = 0;
+    RowTrack tk = row_track_init();
 
     for (long long base = 0; base < m.n; base += 32) {
         const long long i = base + lane;
@@ -77,10 +77,10 @@ __device__ void wide_pass(const DataMeta &m, const Control &c, WideShared &S, in
         if (live) {
             const double yi = __ldg(y + i);
             switch (kind) {
-            case RK_BIN_MLE: RowOp<RK_BIN_MLE>::apply<true, true, true>(eta, yi, rc, w, r, l, bad); break;
-            case RK_POIS: RowOp<RK_POIS>::apply<true, true, true>(eta, yi, rc, w, r, l, bad); break;
-            case RK_BIN_BAYES: RowOp<RK_BIN_BAYES>::apply<true, true, true>(eta, yi, rc, w, r, l, bad); break;
-            default: RowOp<RK_PINIT>::apply<true, true, true>(eta, yi, rc, w, r, l, bad); break;
+            case RK_BIN_MLE: RowOp<RK_BIN_MLE>::apply<true, true, true>(eta, yi, rc, w, r, l, tk); break;
+            case RK_POIS: RowOp<RK_POIS>::apply<true, true, true>(eta, yi, rc, w, r, l, tk); break;
+            case RK_BIN_BAYES: RowOp<RK_BIN_BAYES>::apply<true, true, true>(eta, yi, rc, w, r, l, tk); break;
+            default: RowOp<RK_PINIT>::apply<true, true, true>(eta, yi, rc, w, r, l, tk); break;
             }
         }
         S.wt[lane] = w;
@@ -106,7 +106,14 @@ __device__ void wide_pass(const DataMeta &m, const Control &c, WideShared &S, in
         __syncwarp();
     }
     ll = warp_sum_w(ll);
-    bad = __any_sync(0xffffffffu, bad);
+    int bad_lane;
+    switch (kind) {
+    case RK_BIN_MLE: bad_lane = RowOp<RK_BIN_MLE>::bad_of(tk); break;
+    case RK_POIS: bad_lane = RowOp<RK_POIS>::bad_of(tk); break;
+    case RK_BIN_BAYES: bad_lane = RowOp<RK_BIN_BAYES>::bad_of(tk); break;
+    default: bad_lane = RowOp<RK_PINIT>::bad_of(tk); break;
+    }
+    const int bad = __any_sync(0xffffffffu, bad_lane);
 #pragma unroll
     for (int t = 0; t < PPL; t++) {
         const int pi = lane + 32 * t;

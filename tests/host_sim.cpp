@@ -39,6 +39,7 @@ void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode
     const bool need_g = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_GRAD);
     const bool need_l = (mode == PASS_FULL || mode == PASS_LL);
     double x[MAXK];
+    RowTrack tk = row_track_init();
     for (long long i = 0; i < m.n; i++) {
         double eta = 0.0;
         for (int j = 0; j < k; j++) {
@@ -48,9 +49,9 @@ void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode
         double w = 0.0, r = 0.0, l = 0.0;
         // the kernels decide per warp step (vote) whether rho is evaluated; row by row here
         const bool need_rho = eta >= BIN_RHO_ETA;
-        if (need_l && (need_h || need_g)) RowOp<KIND>::template apply<true, true, true>(eta, y[i], rc, w, r, l, a.bad, need_rho);
-        else if (need_l) RowOp<KIND>::template apply<false, false, true>(eta, y[i], rc, w, r, l, a.bad, need_rho);
-        else RowOp<KIND>::template apply<true, true, false>(eta, y[i], rc, w, r, l, a.bad, need_rho);
+        if (need_l && (need_h || need_g)) RowOp<KIND>::template apply<true, true, true>(eta, y[i], rc, w, r, l, tk, need_rho);
+        else if (need_l) RowOp<KIND>::template apply<false, false, true>(eta, y[i], rc, w, r, l, tk, need_rho);
+        else RowOp<KIND>::template apply<true, true, false>(eta, y[i], rc, w, r, l, tk, need_rho);
         if (need_h)
             for (int p = 0; p < k; p++)
                 for (int q = p; q < k; q++) a.H[tri(p, q, k)] += w * x[p] * x[q];
@@ -58,6 +59,7 @@ void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode
             for (int p = 0; p < k; p++) a.g[p] += r * x[p];
         if (need_l) a.ll += l;
     }
+    a.bad = RowOp<KIND>::bad_of(tk);
 }
 
 void run_pass(const DataMeta &m, const FitDesc &d, const Control &c, const FitState &s, int mode, PassAcc &a)

@@ -24,7 +24,7 @@ def test_fast_exp_about_one_ulp_over_the_working_range():
     ref = np.exp(t.astype(np.longdouble))
     ulp = np.spacing(np.exp(t))
     err = np.abs((got.astype(np.longdouble) - ref) / ulp.astype(np.longdouble)).astype(np.float64)
-    assert err.max() < 1.3, err.max()       # table entry rounding + final fma + degree-5 truncation (0.2 ulp)
+    assert err.max() < 1.35, err.max()      # table entry rounding + final fma + truncation and 21-bit c4, c5 (0.25 ulp)
     assert np.mean(err) < 0.35
 
 
