@@ -167,6 +167,7 @@ __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const do
         }
         acc_sm->ll = ll;
         acc_sm->bad = bad;
+        acc_sm->has_gl = 0;
     }
 }
 
@@ -293,6 +294,7 @@ __device__ __forceinline__ void warp_pass_staged(const double *__restrict__ y, c
         }
         acc_sm->ll = ll;
         acc_sm->bad = bad;
+        acc_sm->has_gl = 0;
     }
 }
 
@@ -405,6 +407,7 @@ __device__ __forceinline__ void warp_pass_pois(const double *const (&cp)[MAXK], 
             acc_sm->ll = 0.0;
         }
         acc_sm->bad = bad;
+        acc_sm->has_gl = 0;
     }
 }
 
@@ -447,6 +450,7 @@ __device__ __forceinline__ void warp_pass_bin(const double *__restrict__ y, cons
     for (int j = 0; j < K; j++) S[j] = 0.0;
     RowTrack tk = row_track_init();
     const double dbp = rc.bp1 - rc.bp0;
+    int any_rho = 0; // some row of this pass had eta >= BIN_RHO_ETA: the reference's rho noise is in play
 
     // x[0] unused (intercept); yp points at this row's response, read only on the rho path
     auto row = [&](const double (&x)[K], const double *yp, bool vote) {
@@ -460,6 +464,7 @@ __device__ __forceinline__ void warp_pass_bin(const double *__restrict__ y, cons
             const double d = 1.0 + e;
             if (NEED_H || NEED_G) {
                 const bool need_rho = vote ? __any_sync(0xffffffffu, eta >= BIN_RHO_ETA) : true;
+                any_rho |= vote ? (int)need_rho : (int)(eta >= BIN_RHO_ETA);
                 if (need_rho) {
                     const double g = fast_rcp(d);
                     const double gp = e * g * g;
@@ -553,6 +558,7 @@ __device__ __forceinline__ void warp_pass_bin(const double *__restrict__ y, cons
     }
     if (NEED_L) L = warp_sum(L);
     const int bad = __any_sync(0xffffffffu, RowOp<KIND>::bad_of(tk));
+    any_rho = __any_sync(0xffffffffu, any_rho);
     if (lane == 0) {
         if (NEED_H) {
 #pragma unroll
@@ -560,8 +566,10 @@ __device__ __forceinline__ void warp_pass_bin(const double *__restrict__ y, cons
         }
         if (NEED_G) {
 #pragma unroll
-            for (int j = 0; j < K; j++)
+            for (int j = 0; j < K; j++) {
                 acc_sm->g[j] = MLE_ ? fma(dbp, xty[j], rc.bp0 * xt1[j]) - S[j] : xty[j] - S[j];
+                if (MLE_) acc_sm->gl[j] = xty[j] - S[j]; // X'(y - g) up to the rho correction (~1e-11 of it)
+            }
         }
         double ll = 0.0;
         if (NEED_L) {
@@ -571,6 +579,7 @@ __device__ __forceinline__ void warp_pass_bin(const double *__restrict__ y, cons
         }
         acc_sm->ll = ll;
         acc_sm->bad = bad;
+        acc_sm->has_gl = (MLE_ && NEED_G && !any_rho) ? 1 : 0; // solver.cuh: shortcuts only for fits free of rho noise
     }
 }
 

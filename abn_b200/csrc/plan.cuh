@@ -207,6 +207,7 @@ ABN_HD void gauss_gram_acc(const DataMeta &m, const FitDesc &d, PassAcc &a)
     }
     a.ll = m.G[gy * m.D + gy];
     a.bad = 0;
+    a.has_gl = 0;
 }
 
 // First IRLS iteration of the binomial mle from the Gram matrix: the reference starts at x = 0
@@ -227,6 +228,7 @@ ABN_HD void binomial_first_acc(const DataMeta &m, const FitDesc &d, PassAcc &a)
     }
     a.ll = -(double)m.n * 0.693147180559945309417; // loglik at eta = 0 (only used if max.iters = 1)
     a.bad = 0;
+    a.has_gl = 0;
 }
 
 // Start values of the Poisson mle (irls_poisson_fast.cpp:37-52) from precomputed moments: the
@@ -244,6 +246,7 @@ ABN_HD void poisson_init_acc(const DataMeta &m, const FitDesc &d, int child, Pas
     }
     a.ll = 0.0;
     a.bad = 0;
+    a.has_gl = 0;
 }
 
 // common state setup
@@ -254,6 +257,7 @@ ABN_HD void state_setup(const DataMeta &m, const FitDesc &d, int child, const Co
     s.M = d.k + ((c.method == BAYES && d.family == GAUSSIAN) ? 1 : 0);
     s.n = (double)m.n;
     s.lfact = m.node_lfact[child];
+    s.icpt = (d.k > 0 && d.cols[0] < 0) ? 1 : 0;
 }
 
 // MDL of a scored mle row: bic + (1 + #selected stored columns - num.na) * log(nvars), _mle.R:343

@@ -123,7 +123,7 @@ __device__ void wide_pass(const DataMeta &m, const Control &c, WideShared &S, in
         }
     }
     if (lane < k) S.acc.g[lane] = gacc;
-    if (lane == 0) { S.acc.ll = ll; S.acc.bad = bad; }
+    if (lane == 0) { S.acc.ll = ll; S.acc.bad = bad; S.acc.has_gl = 0; }
     __syncwarp();
 }
 

@@ -40,6 +40,7 @@ void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode
     const bool need_l = (mode == PASS_FULL || mode == PASS_LL);
     double x[MAXK];
     RowTrack tk = row_track_init();
+    bool any_rho = false;
     for (long long i = 0; i < m.n; i++) {
         double eta = 0.0;
         for (int j = 0; j < k; j++) {
@@ -49,6 +50,7 @@ void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode
         double w = 0.0, r = 0.0, l = 0.0;
         // the kernels decide per warp step (vote) whether rho is evaluated; row by row here
         const bool need_rho = eta >= BIN_RHO_ETA;
+        any_rho |= need_rho;
         if (need_l && (need_h || need_g)) RowOp<KIND>::template apply<true, true, true>(eta, y[i], rc, w, r, l, tk, need_rho);
         else if (need_l) RowOp<KIND>::template apply<false, false, true>(eta, y[i], rc, w, r, l, tk, need_rho);
         else RowOp<KIND>::template apply<true, true, false>(eta, y[i], rc, w, r, l, tk, need_rho);
@@ -57,9 +59,14 @@ void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode
                 for (int q = p; q < k; q++) a.H[tri(p, q, k)] += w * x[p] * x[q];
         if (need_g)
             for (int p = 0; p < k; p++) a.g[p] += r * x[p];
+        if (need_g && KIND == RK_BIN_MLE) { // X'(y - g) for the Taylor finish (solver.cuh "IRLS shortcuts")
+            const double gi = 1.0 / (1.0 + std::exp(-eta));
+            for (int p = 0; p < k; p++) a.gl[p] += (y[i] - gi) * x[p];
+        }
         if (need_l) a.ll += l;
     }
     a.bad = RowOp<KIND>::bad_of(tk);
+    a.has_gl = (need_g && KIND == RK_BIN_MLE && !any_rho) ? 1 : 0;
 }
 
 void run_pass(const DataMeta &m, const FitDesc &d, const Control &c, const FitState &s, int mode, PassAcc &a)

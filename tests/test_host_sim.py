@@ -64,12 +64,14 @@ def test_mle_ex1_config1():
         assert (np.isnan(sim[k]) == np.isnan(ref[k])).all()
     assert (sim["status"] == ref["status"]).all() and (ref["status"] == 2).sum() == 8
     fam = P.node_family[ch]
-    # data passes: the IRLS iterations of the reference minus the first one (taken from the Gram
-    # matrix, plan.cuh binomial_first_acc), plus at most one loglik-only pass when the converging
-    # iteration had not been predicted (solver.cuh PH_MLE_BIN)
-    b = (fam == capi.BINOMIAL) & (ref["status"] == 0)
-    extra = sim["iters"][b] - ref["iters"][b]
-    assert ((extra == -1) | (extra == 0)).all() and (extra == -1).mean() > 0.5
+    # data passes never exceed the reference's IRLS iterations: the first binomial iteration comes
+    # from the Gram matrix (plan.cuh binomial_first_acc) and the confirming last iterations are
+    # replaced by a Taylor step under per-fit error budgets (solver.cuh "IRLS shortcuts")
+    ok = ref["status"] == 0
+    for f in (capi.BINOMIAL, capi.POISSON):
+        b = (fam == f) & ok
+        extra = sim["iters"][b] - ref["iters"][b]
+        assert (extra <= 0).all() and (extra <= -1).mean() > 0.5, f
 
 
 def test_mle_rank_deficient_binomial_drops_leading_columns():
