@@ -2,6 +2,10 @@
 // Gram-only Gaussian kernels and the dispatch of the streaming fit kernels.
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -30,6 +34,50 @@ static_assert(MN_MAXL == MN_MAXL_, "plan.cuh and solver_mn.cuh disagree on the m
 // ---------------------------------------------------------------------------------------------
 // error plumbing
 // ---------------------------------------------------------------------------------------------
+// Device memory comes from the device's default stream-ordered pool with the release threshold
+// lifted, so the buffers of a finished call stay cached in the process and the next one-shot
+// call (abn_b200_score_cache: create + score + destroy) pays neither cudaMalloc nor the page
+// unmapping of cudaFree - measured at 5..30 ms and 3..380 ms per call for a 0.8 GB data set.
+static cudaError_t dev_alloc(void **p, size_t bytes, cudaStream_t s)
+{
+    cudaError_t e = cudaMallocAsync(p, bytes, s);
+    // ABN_B200_FILL=<byte>: fill every new allocation (debugging reads of memory never written)
+    static int fill = -2;
+    if (fill == -2) { const char *v = std::getenv("ABN_B200_FILL"); fill = v ? std::atoi(v) : -1; }
+    if (e == cudaSuccess && fill >= 0) e = cudaMemsetAsync(*p, fill, bytes, s);
+    return e;
+}
+template <typename T>
+static cudaError_t dev_alloc(T **p, size_t bytes, cudaStream_t s) { return dev_alloc(reinterpret_cast<void **>(p), bytes, s); }
+static void dev_free(void *p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
+static void keep_pool(int device)
+{
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    done[device] = true;
+}
+
+// ABN_B200_TRACE=1: wall-clock phases of the host-side calls on stderr (profiles/, bench.py e2e)
+struct PhaseTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    explicit PhaseTrace() : on(std::getenv("ABN_B200_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void mark(const char *what)
+    {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[abn_b200] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 static int fail(char *err, size_t errlen, int code, const char *fmt, ...)
 {
     if (err && errlen) {
@@ -169,6 +217,10 @@ __global__ void gram_reduce(int D, int T, int NP, int chunks, const double *__re
     const int J = I + p;
     const int i = I * GT + st / GT, j = J * GT + st % GT;
     if (i >= D || j >= D) return;
+    // diagonal tiles hold (i, j) and (j, i) both; in a weighted Gram the two sums round differently
+    // ((z_i w) z_j vs (z_j w) z_i), so only the upper element is used and mirrored: symmetric, and no
+    // two threads write the same entry
+    if (I == J && i > j) return;
     double s = 0.0;
     for (int c = 0; c < chunks; c++) s += part[((long long)c * NP + pair) * (GT * GT) + st];
     G[(long long)i * D + j] = s;
@@ -298,9 +350,9 @@ struct abn_data {
 
 static void free_scratch(abn_data *d)
 {
-    cudaFree(d->dChild); cudaFree(d->dParents); cudaFree(d->dIdx); cudaFree(d->dIdxSorted);
-    cudaFree(d->dStatus); cudaFree(d->dIters); cudaFree(d->dKeys); cudaFree(d->dKeysSorted);
-    cudaFree(d->dDescs); cudaFree(d->dRes); cudaFree(d->dSortTmp);
+    dev_free(d->dChild, d->stream); dev_free(d->dParents, d->stream); dev_free(d->dIdx, d->stream); dev_free(d->dIdxSorted, d->stream);
+    dev_free(d->dStatus, d->stream); dev_free(d->dIters, d->stream); dev_free(d->dKeys, d->stream); dev_free(d->dKeysSorted, d->stream);
+    dev_free(d->dDescs, d->stream); dev_free(d->dRes, d->stream); dev_free(d->dSortTmp, d->stream);
     d->dChild = d->dParents = d->dIdx = d->dIdxSorted = d->dStatus = d->dIters = nullptr;
     d->dKeys = d->dKeysSorted = nullptr; d->dDescs = nullptr; d->dRes = nullptr; d->dSortTmp = nullptr;
     d->cap_rows = 0; d->cap_width = 0; d->sortTmpBytes = 0;
@@ -310,13 +362,16 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
 {
     if (!d) return;
     cudaSetDevice(d->device);
+    PhaseTrace tr;
     free_scratch(d);
-    cudaFree(d->dX); cudaFree(d->dG); cudaFree(d->dLfact); cudaFree(d->dFamily); cudaFree(d->dCol0);
-    cudaFree(d->dGw); cudaFree(d->dGwIndex);
-    cudaFree(d->dBucketStart); cudaFree(d->dCounters);
+    dev_free(d->dX, d->stream); dev_free(d->dG, d->stream); dev_free(d->dLfact, d->stream); dev_free(d->dFamily, d->stream); dev_free(d->dCol0, d->stream);
+    dev_free(d->dGw, d->stream); dev_free(d->dGwIndex, d->stream);
+    dev_free(d->dBucketStart, d->stream); dev_free(d->dCounters, d->stream);
+    cudaStreamSynchronize(d->stream); // the frees above are stream-ordered
     if (d->stream) cudaStreamDestroy(d->stream);
     for (auto &ss : d->side) if (ss) cudaStreamDestroy(ss);
     delete d;
+    tr.mark("destroy");
 }
 
 // nmat Gram matrices in one launch: Dz columns of Z; matrix z is weighted by (y_wnodes[z] + 0.1)
@@ -340,7 +395,7 @@ static int launch_gram(abn_data *d, int Dz, const int *wnodes, int nmat, double 
     chunks = (int)((m.n + rpc - 1) / rpc);
     if (chunks < 1) chunks = 1;
     double *part = nullptr;
-    CUDA_TRY(cudaMalloc(&part, (size_t)nmat * chunks * NP * GT * GT * sizeof(double)));
+    CUDA_TRY(dev_alloc(&part, (size_t)nmat * chunks * NP * GT * GT * sizeof(double), d->stream));
     const size_t smem = (size_t)RC * (Dp + 1) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
     if (e == cudaSuccess) {
@@ -348,7 +403,7 @@ static int launch_gram(abn_data *d, int Dz, const int *wnodes, int nmat, double 
         gram_reduce<<<dim3((NP * GT * GT + 255) / 256, nmat), 256, 0, d->stream>>>(Dz, T, NP, chunks, part, dst);
         e = cudaStreamSynchronize(d->stream);
     }
-    cudaFree(part);
+    dev_free(part, d->stream);
     CUDA_TRY(e);
     CUDA_TRY(cudaGetLastError());
     d->timing.launches += 2;
@@ -377,10 +432,12 @@ static int ensure_weighted_grams(abn_data *d, char *err, size_t errlen)
     for (int v = 0; v < m.n_nodes; v++) if (d->family[v] == ABN_POISSON) nodes.push_back(v); // order = gw_index
     if (!nodes.empty()) {
         int *dNodes = nullptr;
-        CUDA_TRY(cudaMalloc(&dNodes, nodes.size() * sizeof(int)));
-        cudaError_t e = cudaMemcpy(dNodes, nodes.data(), nodes.size() * sizeof(int), cudaMemcpyHostToDevice);
+        CUDA_TRY(dev_alloc(&dNodes, nodes.size() * sizeof(int), d->stream));
+        // on the stream the Gram kernels run on: a synchronous cudaMemcpy from pageable memory may return
+        // before its DMA lands and is ordered only against the legacy stream
+        cudaError_t e = cudaMemcpyAsync(dNodes, nodes.data(), nodes.size() * sizeof(int), cudaMemcpyHostToDevice, d->stream);
         int rc = (e == cudaSuccess) ? launch_gram(d, m.D0, dNodes, (int)nodes.size(), d->dGw, err, errlen) : ABN_ERR_CUDA;
-        cudaFree(dNodes);
+        dev_free(dNodes, d->stream);
         CUDA_TRY(e);
         if (rc != ABN_OK) return rc;
     }
@@ -412,6 +469,8 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     }
     if (device < 0 || device >= ndev) return fail(err, errlen, ABN_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
     CUDA_TRY(cudaSetDevice(device));
+    keep_pool(device);
+    PhaseTrace tr;
     abn_data *d = new (std::nothrow) abn_data();
     if (!d) return fail(err, errlen, ABN_ERR_ALLOC, "out of host memory");
     d->device = device;
@@ -440,15 +499,16 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     } while (0)
     TRY_OR_FREE(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     for (auto &ss : d->side) TRY_OR_FREE(cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking));
-    TRY_OR_FREE(cudaMalloc(&d->dX, (size_t)ld * ds->n_cols * sizeof(double)));
-    TRY_OR_FREE(cudaMalloc(&d->dG, (size_t)D * D * sizeof(double)));
-    TRY_OR_FREE(cudaMalloc(&d->dLfact, (size_t)ds->n_nodes * sizeof(double)));
-    TRY_OR_FREE(cudaMalloc(&d->dFamily, (size_t)ds->n_nodes * sizeof(int)));
-    TRY_OR_FREE(cudaMalloc(&d->dCol0, (size_t)(ds->n_nodes + 1) * sizeof(int)));
-    TRY_OR_FREE(cudaMalloc(&d->dGwIndex, (size_t)ds->n_nodes * sizeof(int)));
-    TRY_OR_FREE(cudaMalloc(&d->dGw, std::max<size_t>(1, (size_t)n_pois * D0 * D0) * sizeof(double)));
-    TRY_OR_FREE(cudaMalloc(&d->dBucketStart, (size_t)(NBUCKETS + 1) * sizeof(int)));
-    TRY_OR_FREE(cudaMalloc(&d->dCounters, (size_t)(NBUCKETS + 1) * sizeof(int)));
+    TRY_OR_FREE(dev_alloc(&d->dX, (size_t)ld * ds->n_cols * sizeof(double), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dG, (size_t)D * D * sizeof(double), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dLfact, (size_t)ds->n_nodes * sizeof(double), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dFamily, (size_t)ds->n_nodes * sizeof(int), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dCol0, (size_t)(ds->n_nodes + 1) * sizeof(int), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dGwIndex, (size_t)ds->n_nodes * sizeof(int), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dGw, std::max<size_t>(1, (size_t)n_pois * D0 * D0) * sizeof(double), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dBucketStart, (size_t)(NBUCKETS + 1) * sizeof(int), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dCounters, (size_t)(NBUCKETS + 1) * sizeof(int), d->stream));
+    tr.mark("create: streams + cudaMalloc");
     TRY_OR_FREE(cudaMemsetAsync(d->dX, 0, (size_t)ld * ds->n_cols * sizeof(double), d->stream));
     TRY_OR_FREE(cudaMemcpy2DAsync(d->dX, (size_t)ld * sizeof(double), ds->X, (size_t)ds->n * sizeof(double),
                                   (size_t)ds->n * sizeof(double), (size_t)ds->n_cols, cudaMemcpyHostToDevice, d->stream));
@@ -456,6 +516,7 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     TRY_OR_FREE(cudaMemcpyAsync(d->dCol0, ds->node_col0, (size_t)(ds->n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, d->stream));
     TRY_OR_FREE(cudaMemcpyAsync(d->dGwIndex, d->gw_index.data(), (size_t)ds->n_nodes * sizeof(int), cudaMemcpyHostToDevice, d->stream));
     TRY_OR_FREE(cudaStreamSynchronize(d->stream));
+    tr.mark("create: upload");
 #undef TRY_OR_FREE
     d->m.n = ds->n;
     d->m.ld = ld;
@@ -472,6 +533,7 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     d->m.D0 = D0;
     rc = compute_gram(d, err, errlen);
     if (rc != ABN_OK) { abn_b200_data_destroy(d); return rc; }
+    tr.mark("create: Gram + lfact");
     *out = d;
     return ABN_OK;
 }
@@ -482,19 +544,19 @@ static int ensure_scratch(abn_data *d, long long rows, int width, char *err, siz
     free_scratch(d);
     const long long cap = std::max<long long>(rows, 1024);
     const int w = std::max(width, 1);
-    CUDA_TRY(cudaMalloc(&d->dChild, (size_t)cap * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d->dParents, (size_t)cap * w * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d->dIdx, (size_t)cap * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d->dIdxSorted, (size_t)cap * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d->dStatus, (size_t)cap * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d->dIters, (size_t)cap * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d->dKeys, (size_t)cap));
-    CUDA_TRY(cudaMalloc(&d->dKeysSorted, (size_t)cap));
-    CUDA_TRY(cudaMalloc(&d->dDescs, (size_t)cap * sizeof(FitDesc)));
-    CUDA_TRY(cudaMalloc(&d->dRes, (size_t)cap * 4 * sizeof(double)));
+    CUDA_TRY(dev_alloc(&d->dChild, (size_t)cap * sizeof(int), d->stream));
+    CUDA_TRY(dev_alloc(&d->dParents, (size_t)cap * w * sizeof(int), d->stream));
+    CUDA_TRY(dev_alloc(&d->dIdx, (size_t)cap * sizeof(int), d->stream));
+    CUDA_TRY(dev_alloc(&d->dIdxSorted, (size_t)cap * sizeof(int), d->stream));
+    CUDA_TRY(dev_alloc(&d->dStatus, (size_t)cap * sizeof(int), d->stream));
+    CUDA_TRY(dev_alloc(&d->dIters, (size_t)cap * sizeof(int), d->stream));
+    CUDA_TRY(dev_alloc(&d->dKeys, (size_t)cap, d->stream));
+    CUDA_TRY(dev_alloc(&d->dKeysSorted, (size_t)cap, d->stream));
+    CUDA_TRY(dev_alloc(&d->dDescs, (size_t)cap * sizeof(FitDesc), d->stream));
+    CUDA_TRY(dev_alloc(&d->dRes, (size_t)cap * 4 * sizeof(double), d->stream));
     size_t tmp = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d->dKeys, d->dKeysSorted, d->dIdx, d->dIdxSorted, (int)cap, 0, 8, d->stream));
-    CUDA_TRY(cudaMalloc(&d->dSortTmp, tmp));
+    CUDA_TRY(dev_alloc(&d->dSortTmp, tmp, d->stream));
     d->sortTmpBytes = tmp;
     d->cap_rows = cap;
     d->cap_width = w;
@@ -526,12 +588,14 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
         }
     }
     CUDA_TRY(cudaSetDevice(d->device));
+    PhaseTrace tr;
     int rc = ensure_scratch(d, rows, width, err, errlen);
     if (rc != ABN_OK) return rc;
     if (ctrl->method == ABN_METHOD_MLE) {
         rc = ensure_weighted_grams(d, err, errlen);
         if (rc != ABN_OK) return rc;
     }
+    tr.mark("score: scratch + weighted Grams");
 
     cudaEvent_t ev[5];
     for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
@@ -666,6 +730,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     CUDA_TRY(cudaEventRecord(ev[4], s));
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
+    tr.mark("score: upload + plan + fits + download");
 
     float ms[4] = {0, 0, 0, 0};
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
@@ -702,6 +767,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     for (auto &e : kev0) cudaEventDestroy(e);
     for (auto &e : kev1) cudaEventDestroy(e);
     for (auto &e : ev) cudaEventDestroy(e);
+    tr.mark("score: timing bookkeeping");
     if (n_unsupported > 0 && n_unsupported == rows)
         return fail(err, errlen, ABN_ERR_LIMIT, "no candidate could be scored by the fast kernels");
     return ABN_OK;
@@ -750,4 +816,19 @@ extern "C" void abn_b200_default_control(int32_t method, abn_control *c)
     c->solver = ABN_SOLVER_HYBRID;
     c->device = 0;
     c->nvars = 0;
+}
+
+// test hook (not part of include/abn_b200.h): (re)compute the weighted Gram matrices of the Poisson
+// children and copy them to the host - tests/test_gpu_parity.py checks symmetry and reproducibility
+extern "C" int abn_b200_debug_gw(abn_data *d, double *out, int recompute)
+{
+    if (!d || !out) return ABN_ERR_ARG;
+    cudaSetDevice(d->device);
+    char err[256] = "";
+    if (recompute) d->gw_ready = false;
+    if (ensure_weighted_grams(d, err, sizeof err) != ABN_OK) return ABN_ERR_CUDA;
+    int n_pois = 0;
+    for (int f : d->family) if (f == ABN_POISSON) n_pois++;
+    cudaMemcpy(out, d->dGw, (size_t)n_pois * d->m.D0 * d->m.D0 * 8, cudaMemcpyDeviceToHost);
+    return cudaGetLastError() == cudaSuccess ? ABN_OK : ABN_ERR_CUDA;
 }

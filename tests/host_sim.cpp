@@ -71,6 +71,9 @@ void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode
 
 void run_pass(const DataMeta &m, const FitDesc &d, const Control &c, const FitState &s, int mode, PassAcc &a)
 {
+#if defined(ABN_TRACE_STEPS)
+    fprintf(stderr, "PASS fam %d mode %d\n", d.family, mode);
+#endif
     if (mode == PASS_PINIT) { host_pass<RK_PINIT>(m, d, s.x, PASS_HG, a); return; }
     if (d.family == POISSON) { host_pass<RK_POIS>(m, d, s.x, mode, a); return; }
     if (c.method == MLE) host_pass<RK_BIN_MLE>(m, d, s.x, mode, a);
