@@ -128,10 +128,10 @@ __device__ __forceinline__ double z_value(const DataMeta &m, int a, long long i)
 {
     if (a == 0) return 1.0;
     if (a <= m.n_cols) return __ldg(m.X + (long long)(a - 1) * m.ld + i);
-    int node = a - 1 - m.n_cols;
-    const bool wz0 = node >= m.n_nodes; // second block of virtual columns: W0 z0 of the Poisson mle start
-    if (wz0) node -= m.n_nodes;
-    if (m.node_family[node] != POISSON) return 0.0;
+    int o = a - 1 - m.n_cols;
+    const bool wz0 = o >= m.n_pois; // second block of virtual columns: W0 z0 of the Poisson mle start
+    if (wz0) o -= m.n_pois;
+    const int node = m.pois_node[o];
     const double y = __ldg(m.X + (long long)m.node_col0[node] * m.ld + i);
     const double mu = y + 0.1, eta0 = log(mu);
     return wz0 ? fma(mu, eta0, y - mu) : eta0;
@@ -169,16 +169,14 @@ gram_partial(const DataMeta m, int Dz, const int *__restrict__ wnodes, int T, in
     for (long long base = r0; base < r1; base += RC) {
         const int nr = (int)min((long long)RC, r1 - base);
         __syncthreads();
-        // coalesced along rows within a column; transposed store
+        // coalesced along rows within a column; transposed store. Each GT-column tile is padded to GT + 1
+        // slots: consecutive threads read consecutive J tiles of the same row, and a stride of GT = 6
+        // doubles (12 banks) is a 4-way bank conflict where 7 doubles (14 banks) is conflict-free for
+        // 64-bit loads. Columns past Dz in the last tile are staged as zeros.
         double *ws = zs + (size_t)RC * Dp;
-        for (int e = threadIdx.x; e < RC * Dz; e += GRAM_THREADS) {
+        for (int e = threadIdx.x; e < RC * T * GT; e += GRAM_THREADS) {
             const int col = e / RC, r = e - col * RC;
-            zs[r * Dp + col] = (r < nr) ? z_value(m, col, base + r) : 0.0;
-        }
-        // zero the padding columns the last tile may touch
-        for (int e = threadIdx.x; e < RC * (Dp - Dz); e += GRAM_THREADS) {
-            const int r = e / (Dp - Dz), col = Dz + (e - r * (Dp - Dz));
-            zs[r * Dp + col] = 0.0;
+            zs[r * Dp + (col / GT) * (GT + 1) + col % GT] = (col < Dz && r < nr) ? z_value(m, col, base + r) : 0.0;
         }
         for (int r = threadIdx.x; r < RC; r += GRAM_THREADS)
             ws[r] = (wnode >= 0 && r < nr) ? __ldg(m.X + (long long)m.node_col0[wnode] * m.ld + base + r) + 0.1 : 1.0;
@@ -188,7 +186,7 @@ gram_partial(const DataMeta m, int Dz, const int *__restrict__ wnodes, int T, in
                 double a[GT], b[GT];
                 const double wr = ws[r];
 #pragma unroll
-                for (int t = 0; t < GT; t++) { a[t] = zs[r * Dp + I * GT + t] * wr; b[t] = zs[r * Dp + J * GT + t]; }
+                for (int t = 0; t < GT; t++) { a[t] = zs[r * Dp + I * (GT + 1) + t] * wr; b[t] = zs[r * Dp + J * (GT + 1) + t]; }
 #pragma unroll
                 for (int s = 0; s < GT; s++)
 #pragma unroll
@@ -328,7 +326,7 @@ struct abn_data {
     int device = 0;
     DataMeta m{};
     double *dX = nullptr, *dG = nullptr, *dLfact = nullptr, *dGw = nullptr;
-    int *dFamily = nullptr, *dCol0 = nullptr, *dGwIndex = nullptr;
+    int *dFamily = nullptr, *dCol0 = nullptr, *dGwIndex = nullptr, *dPoisNode = nullptr;
     std::vector<int> family, col0, gw_index;
     bool gw_ready = false;
     int sm_count = 148;
@@ -365,7 +363,7 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
     PhaseTrace tr;
     free_scratch(d);
     dev_free(d->dX, d->stream); dev_free(d->dG, d->stream); dev_free(d->dLfact, d->stream); dev_free(d->dFamily, d->stream); dev_free(d->dCol0, d->stream);
-    dev_free(d->dGw, d->stream); dev_free(d->dGwIndex, d->stream);
+    dev_free(d->dGw, d->stream); dev_free(d->dGwIndex, d->stream); dev_free(d->dPoisNode, d->stream);
     dev_free(d->dBucketStart, d->stream); dev_free(d->dCounters, d->stream);
     cudaStreamSynchronize(d->stream); // the frees above are stream-ordered
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -381,7 +379,7 @@ static int launch_gram(abn_data *d, int Dz, const int *wnodes, int nmat, double 
     const DataMeta &m = d->m;
     const int T = (Dz + GT - 1) / GT;
     const int NP = T * (T + 1) / 2;
-    const int Dp = T * GT + 1; // padded smem row, odd-ish stride
+    const int Dp = (T * (GT + 1)) | 1; // padded smem row: GT + 1 slots per tile, odd stride (conflict-free transposed stores)
     int RC = 64;
     while (RC > 8 && (size_t)RC * (Dp + 1) * sizeof(double) > 160 * 1024) RC >>= 1;
     if ((size_t)RC * (Dp + 1) * sizeof(double) > 200 * 1024)
@@ -480,11 +478,12 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     d->col0.assign(ds->node_col0, ds->node_col0 + ds->n_nodes + 1);
 
     const long long ld = ((ds->n + 15) / 16) * 16; // 128-byte aligned columns
-    const int D = 1 + ds->n_cols + 2 * ds->n_nodes;
     const int D0 = 1 + ds->n_cols;
     int n_pois = 0;
     d->gw_index.assign(ds->n_nodes, -1);
-    for (int i = 0; i < ds->n_nodes; i++) if (ds->node_family[i] == ABN_POISSON) d->gw_index[i] = n_pois++;
+    std::vector<int> pois_node;
+    for (int i = 0; i < ds->n_nodes; i++) if (ds->node_family[i] == ABN_POISSON) { d->gw_index[i] = n_pois++; pois_node.push_back(i); }
+    const int D = 1 + ds->n_cols + 2 * n_pois; // [1 | X | log(y + 0.1) | W0 z0] of the Poisson nodes
     int rc = ABN_OK;
 #define TRY_OR_FREE(expr)                                                       \
     do {                                                                        \
@@ -505,6 +504,7 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     TRY_OR_FREE(dev_alloc(&d->dFamily, (size_t)ds->n_nodes * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dCol0, (size_t)(ds->n_nodes + 1) * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dGwIndex, (size_t)ds->n_nodes * sizeof(int), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dPoisNode, std::max<size_t>(1, pois_node.size()) * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dGw, std::max<size_t>(1, (size_t)n_pois * D0 * D0) * sizeof(double), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dBucketStart, (size_t)(NBUCKETS + 1) * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dCounters, (size_t)(NBUCKETS + 1) * sizeof(int), d->stream));
@@ -515,6 +515,7 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     TRY_OR_FREE(cudaMemcpyAsync(d->dFamily, ds->node_family, (size_t)ds->n_nodes * sizeof(int), cudaMemcpyHostToDevice, d->stream));
     TRY_OR_FREE(cudaMemcpyAsync(d->dCol0, ds->node_col0, (size_t)(ds->n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, d->stream));
     TRY_OR_FREE(cudaMemcpyAsync(d->dGwIndex, d->gw_index.data(), (size_t)ds->n_nodes * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    if (n_pois) TRY_OR_FREE(cudaMemcpyAsync(d->dPoisNode, pois_node.data(), pois_node.size() * sizeof(int), cudaMemcpyHostToDevice, d->stream));
     TRY_OR_FREE(cudaStreamSynchronize(d->stream));
     tr.mark("create: upload");
 #undef TRY_OR_FREE
@@ -531,6 +532,8 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     d->m.Gw = d->dGw;
     d->m.node_gw = d->dGwIndex;
     d->m.D0 = D0;
+    d->m.n_pois = n_pois;
+    d->m.pois_node = d->dPoisNode;
     rc = compute_gram(d, err, errlen);
     if (rc != ABN_OK) { abn_b200_data_destroy(d); return rc; }
     tr.mark("create: Gram + lfact");

@@ -15,9 +15,10 @@ namespace ABN_NS {
 
 ABN_HD int gram_icpt() { return 0; }
 ABN_HD int gram_col(int c) { return 1 + c; }
-ABN_HD int gram_logy(const DataMeta &m, int node) { return 1 + m.n_cols + node; }
+// virtual columns exist for Poisson nodes only, in the order of node_gw
+ABN_HD int gram_logy(const DataMeta &m, int node) { return 1 + m.n_cols + m.node_gw[node]; }
 // virtual column W0 z0 = (y + 0.1) log(y + 0.1) + (y - (y + 0.1)) of a Poisson node (start values of the mle)
-ABN_HD int gram_wz0(const DataMeta &m, int node) { return 1 + m.n_cols + m.n_nodes + node; }
+ABN_HD int gram_wz0(const DataMeta &m, int node) { return 1 + m.n_cols + m.n_pois + m.node_gw[node]; }
 
 // one candidate's resolved design
 struct FitDesc {

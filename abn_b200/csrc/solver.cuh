@@ -1005,6 +1005,9 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
         int gst = 0;
         if (s.nslow2 == 5) gst = 28;      // GSL_ENOPROGJ
         else if (s.nslow1 == 10) gst = 27; // GSL_ENOPROG
+#if defined(ABN_TRACE_STEPS) && !defined(__CUDA_ARCH__)
+        { double res = 0; for (int i = 0; i < M; i++) res += fabs(s.f[i]); fprintf(stderr, "HY fam %d iter %d res %.3e ratio %.3f\n", s.family, s.loop_iter, res, ratio); }
+#endif
         int nxt = hy_after_iterate(s, c, gst);
         if (nxt == PASS_GRAD) s.loop_iter++;
         return nxt;

@@ -137,7 +137,10 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
 {
     host_log_table(); // initialise before the parallel region
     const long long n = ds->n;
-    const int D = 1 + ds->n_cols + 2 * ds->n_nodes, D0 = 1 + ds->n_cols;
+    int n_pois = 0;
+    std::vector<int> gw_index(ds->n_nodes, -1), pois_node;
+    for (int v = 0; v < ds->n_nodes; v++) if (ds->node_family[v] == ABN_POISSON) { gw_index[v] = n_pois++; pois_node.push_back(v); }
+    const int D = 1 + ds->n_cols + 2 * n_pois, D0 = 1 + ds->n_cols;
     // Z = [1 | X | log(y + 0.1) of Poisson nodes], G = Z'Z
     std::vector<double> G((size_t)D * D, 0.0), lfact(ds->n_nodes, 0.0);
     std::vector<const double *> zc(D, nullptr);
@@ -146,11 +149,8 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
     zc[0] = ones.data();
     for (int c = 0; c < ds->n_cols; c++) zc[1 + c] = ds->X + (size_t)c * n;
     extra.resize(2 * ds->n_nodes);
-    std::vector<int> gw_index(ds->n_nodes, -1);
-    int n_pois = 0;
     for (int v = 0; v < ds->n_nodes; v++) {
         if (ds->node_family[v] != ABN_POISSON) continue;
-        gw_index[v] = n_pois++;
         const double *y = ds->X + (size_t)ds->node_col0[v] * n;
         extra[v].resize(n);
         extra[ds->n_nodes + v].resize(n);
@@ -160,8 +160,8 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             extra[ds->n_nodes + v][i] = std::fma(mu, eta0, y[i] - mu);
             lfact[v] += std::lgamma(y[i] + 1.0);
         }
-        zc[1 + ds->n_cols + v] = extra[v].data();
-        zc[1 + ds->n_cols + ds->n_nodes + v] = extra[ds->n_nodes + v].data();
+        zc[1 + ds->n_cols + gw_index[v]] = extra[v].data();
+        zc[1 + ds->n_cols + n_pois + gw_index[v]] = extra[ds->n_nodes + v].data();
     }
     // weighted Gram matrices of the Poisson children: Z0' diag(y + 0.1) Z0
     std::vector<double> Gw((size_t)std::max(1, n_pois) * D0 * D0, 0.0);
@@ -186,7 +186,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
         }
     }
     DataMeta m{n, n, ds->n_nodes, ds->n_cols, D, ds->X, G.data(), ds->node_family, ds->node_col0, lfact.data(),
-               Gw.data(), gw_index.data(), D0};
+               Gw.data(), gw_index.data(), D0, n_pois, pois_node.data()};
     Control c{ctrl->method, ctrl->max_iters, ctrl->solver, ctrl->nvars, ctrl->tol, ctrl->epsabs,
               ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale};
 
