@@ -118,7 +118,7 @@ static bool debug_sync()
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// K1: global Gram  G = Z^T Z,  Z = [1 | X | log(y + 0.1) of Poisson nodes], FP64, deterministic
+// K1: global Gram  G = Z^T Z,  Z = [1 | X | log(y + 0.1) of the Poisson nodes], FP64, deterministic
 // ---------------------------------------------------------------------------------------------
 constexpr int GT = 6;        // register tile edge
 constexpr int GRAM_THREADS = 256;
@@ -128,13 +128,8 @@ __device__ __forceinline__ double z_value(const DataMeta &m, int a, long long i)
 {
     if (a == 0) return 1.0;
     if (a <= m.n_cols) return __ldg(m.X + (long long)(a - 1) * m.ld + i);
-    int o = a - 1 - m.n_cols;
-    const bool wz0 = o >= m.n_pois; // second block of virtual columns: W0 z0 of the Poisson mle start
-    if (wz0) o -= m.n_pois;
-    const int node = m.pois_node[o];
-    const double y = __ldg(m.X + (long long)m.node_col0[node] * m.ld + i);
-    const double mu = y + 0.1, eta0 = log(mu);
-    return wz0 ? fma(mu, eta0, y - mu) : eta0;
+    const int node = m.pois_node[a - 1 - m.n_cols]; // virtual column: log(y + 0.1) of a Poisson node (Bayes start values)
+    return log(__ldg(m.X + (long long)m.node_col0[node] * m.ld + i) + 0.1);
 }
 
 // grid.x = row chunks, grid.y = groups of GRAM_THREADS tile pairs. Each thread owns one GT x GT
@@ -142,15 +137,10 @@ __device__ __forceinline__ double z_value(const DataMeta &m, int a, long long i)
 // memory (row-major, padded) and every thread sweeps them. Partial tiles go to
 // part[chunk][pair][GT*GT]; gram_reduce sums the chunks in a fixed order.
 __global__ void __launch_bounds__(GRAM_THREADS)
-gram_partial(const DataMeta m, int Dz, const int *__restrict__ wnodes, int T, int NP, int RC, int Dp,
-             long long rows_per_chunk, double *__restrict__ part)
+gram_partial(const DataMeta m, int Dz, int T, int NP, int RC, int Dp, long long rows_per_chunk,
+             double *__restrict__ part)
 {
-    // blockIdx.z selects one of several weighted Gram matrices computed by the same launch
-    const int wnode = wnodes ? wnodes[blockIdx.z] : -1;
-    part += (long long)blockIdx.z * gridDim.x * NP * (GT * GT);
-    // Dz: columns of Z used (m.D for the global Gram, m.D0 for a weighted one); wnode >= 0: weight
-    // rows by (y_wnode + 0.1) (the Poisson mle start weights of child wnode)
-    extern __shared__ double zs[]; // RC x Dp, then RC weights
+    extern __shared__ double zs[]; // RC x Dp
     const int pair = blockIdx.y * GRAM_THREADS + threadIdx.x;
     int I = 0, J = 0;
     if (pair < NP) { // unrank (I, J), I <= J, row-major over the upper triangle
@@ -173,20 +163,16 @@ gram_partial(const DataMeta m, int Dz, const int *__restrict__ wnodes, int T, in
         // slots: consecutive threads read consecutive J tiles of the same row, and a stride of GT = 6
         // doubles (12 banks) is a 4-way bank conflict where 7 doubles (14 banks) is conflict-free for
         // 64-bit loads. Columns past Dz in the last tile are staged as zeros.
-        double *ws = zs + (size_t)RC * Dp;
         for (int e = threadIdx.x; e < RC * T * GT; e += GRAM_THREADS) {
             const int col = e / RC, r = e - col * RC;
             zs[r * Dp + (col / GT) * (GT + 1) + col % GT] = (col < Dz && r < nr) ? z_value(m, col, base + r) : 0.0;
         }
-        for (int r = threadIdx.x; r < RC; r += GRAM_THREADS)
-            ws[r] = (wnode >= 0 && r < nr) ? __ldg(m.X + (long long)m.node_col0[wnode] * m.ld + base + r) + 0.1 : 1.0;
         __syncthreads();
         if (pair < NP) {
             for (int r = 0; r < nr; r++) {
                 double a[GT], b[GT];
-                const double wr = ws[r];
 #pragma unroll
-                for (int t = 0; t < GT; t++) { a[t] = zs[r * Dp + I * (GT + 1) + t] * wr; b[t] = zs[r * Dp + J * (GT + 1) + t]; }
+                for (int t = 0; t < GT; t++) { a[t] = zs[r * Dp + I * (GT + 1) + t]; b[t] = zs[r * Dp + J * (GT + 1) + t]; }
 #pragma unroll
                 for (int s = 0; s < GT; s++)
 #pragma unroll
@@ -205,8 +191,6 @@ gram_partial(const DataMeta m, int Dz, const int *__restrict__ wnodes, int T, in
 
 __global__ void gram_reduce(int D, int T, int NP, int chunks, const double *__restrict__ part, double *__restrict__ G)
 {
-    part += (long long)blockIdx.y * chunks * NP * (GT * GT);
-    G += (long long)blockIdx.y * D * D;
     const int e = blockIdx.x * blockDim.x + threadIdx.x; // element of a tile pair
     if (e >= NP * GT * GT) return;
     const int pair = e / (GT * GT), st = e - pair * (GT * GT);
@@ -215,9 +199,8 @@ __global__ void gram_reduce(int D, int T, int NP, int chunks, const double *__re
     const int J = I + p;
     const int i = I * GT + st / GT, j = J * GT + st % GT;
     if (i >= D || j >= D) return;
-    // diagonal tiles hold (i, j) and (j, i) both; in a weighted Gram the two sums round differently
-    // ((z_i w) z_j vs (z_j w) z_i), so only the upper element is used and mirrored: symmetric, and no
-    // two threads write the same entry
+    // diagonal tiles hold (i, j) and (j, i) both: only the upper element is used and mirrored, so that no
+    // two threads write the same entry (with row weights the two sums would even round differently)
     if (I == J && i > j) return;
     double s = 0.0;
     for (int c = 0; c < chunks; c++) s += part[((long long)c * NP + pair) * (GT * GT) + st];
@@ -325,10 +308,9 @@ gauss_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ desc
 struct abn_data {
     int device = 0;
     DataMeta m{};
-    double *dX = nullptr, *dG = nullptr, *dLfact = nullptr, *dGw = nullptr;
+    double *dX = nullptr, *dG = nullptr, *dLfact = nullptr;
     int *dFamily = nullptr, *dCol0 = nullptr, *dGwIndex = nullptr, *dPoisNode = nullptr;
     std::vector<int> family, col0, gw_index;
-    bool gw_ready = false;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     static constexpr int NSIDE = 3;
@@ -363,7 +345,7 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
     PhaseTrace tr;
     free_scratch(d);
     dev_free(d->dX, d->stream); dev_free(d->dG, d->stream); dev_free(d->dLfact, d->stream); dev_free(d->dFamily, d->stream); dev_free(d->dCol0, d->stream);
-    dev_free(d->dGw, d->stream); dev_free(d->dGwIndex, d->stream); dev_free(d->dPoisNode, d->stream);
+    dev_free(d->dGwIndex, d->stream); dev_free(d->dPoisNode, d->stream);
     dev_free(d->dBucketStart, d->stream); dev_free(d->dCounters, d->stream);
     cudaStreamSynchronize(d->stream); // the frees above are stream-ordered
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -372,33 +354,31 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
     tr.mark("destroy");
 }
 
-// nmat Gram matrices in one launch: Dz columns of Z; matrix z is weighted by (y_wnodes[z] + 0.1)
-// (wnodes == nullptr: one unweighted matrix); results Dz x Dz each, consecutive at dst
-static int launch_gram(abn_data *d, int Dz, const int *wnodes, int nmat, double *dst, char *err, size_t errlen)
+// G = Z'Z over the Dz columns of Z, result Dz x Dz at dst
+static int launch_gram(abn_data *d, int Dz, double *dst, char *err, size_t errlen)
 {
     const DataMeta &m = d->m;
     const int T = (Dz + GT - 1) / GT;
     const int NP = T * (T + 1) / 2;
     const int Dp = (T * (GT + 1)) | 1; // padded smem row: GT + 1 slots per tile, odd stride (conflict-free transposed stores)
     int RC = 64;
-    while (RC > 8 && (size_t)RC * (Dp + 1) * sizeof(double) > 160 * 1024) RC >>= 1;
-    if ((size_t)RC * (Dp + 1) * sizeof(double) > 200 * 1024)
+    while (RC > 8 && (size_t)RC * Dp * sizeof(double) > 160 * 1024) RC >>= 1;
+    if ((size_t)RC * Dp * sizeof(double) > 200 * 1024)
         return fail(err, errlen, ABN_ERR_LIMIT, "data set has too many columns for the Gram kernel (D=%d)", Dz);
     const int gy = (NP + GRAM_THREADS - 1) / GRAM_THREADS;
-    int chunks = std::max(1, (2 * d->sm_count) / (gy * nmat));
-    if (nmat > 1) chunks = std::max(chunks, 16);
+    int chunks = std::max(1, (2 * d->sm_count) / gy);
     long long rpc = (m.n + chunks - 1) / chunks;
     rpc = ((rpc + RC - 1) / RC) * RC;
     if (rpc < RC) rpc = RC;
     chunks = (int)((m.n + rpc - 1) / rpc);
     if (chunks < 1) chunks = 1;
     double *part = nullptr;
-    CUDA_TRY(dev_alloc(&part, (size_t)nmat * chunks * NP * GT * GT * sizeof(double), d->stream));
-    const size_t smem = (size_t)RC * (Dp + 1) * sizeof(double);
+    CUDA_TRY(dev_alloc(&part, (size_t)chunks * NP * GT * GT * sizeof(double), d->stream));
+    const size_t smem = (size_t)RC * Dp * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
     if (e == cudaSuccess) {
-        gram_partial<<<dim3(chunks, gy, nmat), GRAM_THREADS, smem, d->stream>>>(m, Dz, wnodes, T, NP, RC, Dp, rpc, part);
-        gram_reduce<<<dim3((NP * GT * GT + 255) / 256, nmat), 256, 0, d->stream>>>(Dz, T, NP, chunks, part, dst);
+        gram_partial<<<dim3(chunks, gy), GRAM_THREADS, smem, d->stream>>>(m, Dz, T, NP, RC, Dp, rpc, part);
+        gram_reduce<<<(NP * GT * GT + 255) / 256, 256, 0, d->stream>>>(Dz, T, NP, chunks, part, dst);
         e = cudaStreamSynchronize(d->stream);
     }
     dev_free(part, d->stream);
@@ -411,35 +391,12 @@ static int launch_gram(abn_data *d, int Dz, const int *wnodes, int nmat, double 
 static int compute_gram(abn_data *d, char *err, size_t errlen)
 {
     const DataMeta &m = d->m;
-    int rc = launch_gram(d, m.D, nullptr, 1, d->dG, err, errlen);
+    int rc = launch_gram(d, m.D, d->dG, err, errlen);
     if (rc != ABN_OK) return rc;
     lfact_kernel<<<m.n_nodes, 256, 0, d->stream>>>(m, d->dLfact);
     d->timing.launches += 1;
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     CUDA_TRY(cudaGetLastError());
-    return ABN_OK;
-}
-
-// weighted Gram matrices of the Poisson children (start values of the mle without a data pass):
-// one launch for all of them; computed on the first mle call on a data set, never for bayes
-static int ensure_weighted_grams(abn_data *d, char *err, size_t errlen)
-{
-    if (d->gw_ready) return ABN_OK;
-    const DataMeta &m = d->m;
-    std::vector<int> nodes;
-    for (int v = 0; v < m.n_nodes; v++) if (d->family[v] == ABN_POISSON) nodes.push_back(v); // order = gw_index
-    if (!nodes.empty()) {
-        int *dNodes = nullptr;
-        CUDA_TRY(dev_alloc(&dNodes, nodes.size() * sizeof(int), d->stream));
-        // on the stream the Gram kernels run on: a synchronous cudaMemcpy from pageable memory may return
-        // before its DMA lands and is ordered only against the legacy stream
-        cudaError_t e = cudaMemcpyAsync(dNodes, nodes.data(), nodes.size() * sizeof(int), cudaMemcpyHostToDevice, d->stream);
-        int rc = (e == cudaSuccess) ? launch_gram(d, m.D0, dNodes, (int)nodes.size(), d->dGw, err, errlen) : ABN_ERR_CUDA;
-        dev_free(dNodes, d->stream);
-        CUDA_TRY(e);
-        if (rc != ABN_OK) return rc;
-    }
-    d->gw_ready = true;
     return ABN_OK;
 }
 
@@ -478,12 +435,11 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     d->col0.assign(ds->node_col0, ds->node_col0 + ds->n_nodes + 1);
 
     const long long ld = ((ds->n + 15) / 16) * 16; // 128-byte aligned columns
-    const int D0 = 1 + ds->n_cols;
     int n_pois = 0;
     d->gw_index.assign(ds->n_nodes, -1);
     std::vector<int> pois_node;
     for (int i = 0; i < ds->n_nodes; i++) if (ds->node_family[i] == ABN_POISSON) { d->gw_index[i] = n_pois++; pois_node.push_back(i); }
-    const int D = 1 + ds->n_cols + 2 * n_pois; // [1 | X | log(y + 0.1) | W0 z0] of the Poisson nodes
+    const int D = 1 + ds->n_cols + n_pois; // [1 | X | log(y + 0.1) of the Poisson nodes]
     int rc = ABN_OK;
 #define TRY_OR_FREE(expr)                                                       \
     do {                                                                        \
@@ -505,7 +461,6 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     TRY_OR_FREE(dev_alloc(&d->dCol0, (size_t)(ds->n_nodes + 1) * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dGwIndex, (size_t)ds->n_nodes * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dPoisNode, std::max<size_t>(1, pois_node.size()) * sizeof(int), d->stream));
-    TRY_OR_FREE(dev_alloc(&d->dGw, std::max<size_t>(1, (size_t)n_pois * D0 * D0) * sizeof(double), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dBucketStart, (size_t)(NBUCKETS + 1) * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dCounters, (size_t)(NBUCKETS + 1) * sizeof(int), d->stream));
     tr.mark("create: streams + cudaMalloc");
@@ -529,9 +484,7 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     d->m.node_family = d->dFamily;
     d->m.node_col0 = d->dCol0;
     d->m.node_lfact = d->dLfact;
-    d->m.Gw = d->dGw;
     d->m.node_gw = d->dGwIndex;
-    d->m.D0 = D0;
     d->m.n_pois = n_pois;
     d->m.pois_node = d->dPoisNode;
     rc = compute_gram(d, err, errlen);
@@ -594,11 +547,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     PhaseTrace tr;
     int rc = ensure_scratch(d, rows, width, err, errlen);
     if (rc != ABN_OK) return rc;
-    if (ctrl->method == ABN_METHOD_MLE) {
-        rc = ensure_weighted_grams(d, err, errlen);
-        if (rc != ABN_OK) return rc;
-    }
-    tr.mark("score: scratch + weighted Grams");
+    tr.mark("score: scratch");
 
     cudaEvent_t ev[5];
     for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
@@ -819,19 +768,4 @@ extern "C" void abn_b200_default_control(int32_t method, abn_control *c)
     c->solver = ABN_SOLVER_HYBRID;
     c->device = 0;
     c->nvars = 0;
-}
-
-// test hook (not part of include/abn_b200.h): (re)compute the weighted Gram matrices of the Poisson
-// children and copy them to the host - tests/test_gpu_parity.py checks symmetry and reproducibility
-extern "C" int abn_b200_debug_gw(abn_data *d, double *out, int recompute)
-{
-    if (!d || !out) return ABN_ERR_ARG;
-    cudaSetDevice(d->device);
-    char err[256] = "";
-    if (recompute) d->gw_ready = false;
-    if (ensure_weighted_grams(d, err, sizeof err) != ABN_OK) return ABN_ERR_CUDA;
-    int n_pois = 0;
-    for (int f : d->family) if (f == ABN_POISSON) n_pois++;
-    cudaMemcpy(out, d->dGw, (size_t)n_pois * d->m.D0 * d->m.D0 * 8, cudaMemcpyDeviceToHost);
-    return cudaGetLastError() == cudaSuccess ? ABN_OK : ABN_ERR_CUDA;
 }

@@ -17,8 +17,6 @@ ABN_HD int gram_icpt() { return 0; }
 ABN_HD int gram_col(int c) { return 1 + c; }
 // virtual columns exist for Poisson nodes only, in the order of node_gw
 ABN_HD int gram_logy(const DataMeta &m, int node) { return 1 + m.n_cols + m.node_gw[node]; }
-// virtual column W0 z0 = (y + 0.1) log(y + 0.1) + (y - (y + 0.1)) of a Poisson node (start values of the mle)
-ABN_HD int gram_wz0(const DataMeta &m, int node) { return 1 + m.n_cols + m.n_pois + m.node_gw[node]; }
 
 // one candidate's resolved design
 struct FitDesc {
@@ -232,21 +230,29 @@ ABN_HD void binomial_first_acc(const DataMeta &m, const FitDesc &d, PassAcc &a)
     a.has_gl = 0;
 }
 
-// Start values of the Poisson mle (irls_poisson_fast.cpp:37-52) from precomputed moments: the
-// weights W0 = y + 0.1 depend on the child only, so X'W0X is a block of the child's weighted Gram
-// matrix Gw and X'W0z0 a column of the global Gram (virtual column gram_wz0). No data pass.
+// Start values of the Poisson mle, no data pass. The reference starts from a weighted least-squares fit
+// of log(y + 0.1) (irls_poisson_fast.cpp:37-52), about 0.26 away from the optimum in the scale of
+// the linear predictor on BASELINE's data, and needs two Newton iterations to get within 1e-2. One
+// Newton step from the intercept-only model is a better start and is made of Gram entries alone:
+// at beta = (log ybar, 0, ..., 0) every mean is ybar, so H = ybar X'X and the score is X'(y - ybar):
+//   beta = beta_null + (ybar X'X)^-1 X'(y - ybar)  <=>  solve(H, H beta_null + X'y - ybar X'1)
+// with H beta_null = ybar log(ybar) X'1. It lands 2e-3..2e-2 from the optimum. The iteration
+// converges to the same maximum either way (solver.cuh "IRLS shortcuts" on what that means for
+// parity); an all-zero child (ybar = 0) starts at zero like a failed solve of the reference.
 ABN_HD void poisson_init_acc(const DataMeta &m, const FitDesc &d, int child, PassAcc &a)
 {
+    (void)child;
     const int k = d.k;
-    const double *Gw = m.Gw + (long long)m.node_gw[child] * m.D0 * m.D0;
-    const long long gu = gram_wz0(m, child);
+    const long long gy = gram_col(d.ycol);
+    const double ybar = m.G[gy] / (double)m.n; // G[0][y] = sum y
+    const double c = ybar * (log(ybar) - 1.0);
     for (int i = 0; i < k; i++) {
         const long long gi = gidx(d, i);
-        for (int j = i; j < k; j++) a.H[tri(i, j, k)] = Gw[gi * m.D0 + gidx(d, j)];
-        a.g[i] = m.G[gi * m.D + gu];
+        for (int j = i; j < k; j++) a.H[tri(i, j, k)] = ybar * m.G[gi * m.D + gidx(d, j)];
+        a.g[i] = fma(c, m.G[gi * m.D], m.G[gi * m.D + gy]);
     }
     a.ll = 0.0;
-    a.bad = 0;
+    a.bad = !(ybar > 0.0) || !isfinite(c);
     a.has_gl = 0;
 }
 

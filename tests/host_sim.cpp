@@ -140,7 +140,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
     int n_pois = 0;
     std::vector<int> gw_index(ds->n_nodes, -1), pois_node;
     for (int v = 0; v < ds->n_nodes; v++) if (ds->node_family[v] == ABN_POISSON) { gw_index[v] = n_pois++; pois_node.push_back(v); }
-    const int D = 1 + ds->n_cols + 2 * n_pois, D0 = 1 + ds->n_cols;
+    const int D = 1 + ds->n_cols + n_pois;
     // Z = [1 | X | log(y + 0.1) of Poisson nodes], G = Z'Z
     std::vector<double> G((size_t)D * D, 0.0), lfact(ds->n_nodes, 0.0);
     std::vector<const double *> zc(D, nullptr);
@@ -153,28 +153,12 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
         if (ds->node_family[v] != ABN_POISSON) continue;
         const double *y = ds->X + (size_t)ds->node_col0[v] * n;
         extra[v].resize(n);
-        extra[ds->n_nodes + v].resize(n);
         for (long long i = 0; i < n; i++) {
             const double mu = y[i] + 0.1, eta0 = std::log(mu);
             extra[v][i] = eta0;
-            extra[ds->n_nodes + v][i] = std::fma(mu, eta0, y[i] - mu);
             lfact[v] += std::lgamma(y[i] + 1.0);
         }
         zc[1 + ds->n_cols + gw_index[v]] = extra[v].data();
-        zc[1 + ds->n_cols + n_pois + gw_index[v]] = extra[ds->n_nodes + v].data();
-    }
-    // weighted Gram matrices of the Poisson children: Z0' diag(y + 0.1) Z0
-    std::vector<double> Gw((size_t)std::max(1, n_pois) * D0 * D0, 0.0);
-    for (int v = 0; v < ds->n_nodes; v++) {
-        if (gw_index[v] < 0) continue;
-        const double *y = ds->X + (size_t)ds->node_col0[v] * n;
-        double *g = Gw.data() + (size_t)gw_index[v] * D0 * D0;
-        for (int a = 0; a < D0; a++)
-            for (int b = a; b < D0; b++) {
-                double s = 0.0;
-                for (long long i = 0; i < n; i++) s += (zc[a][i] * (y[i] + 0.1)) * zc[b][i];
-                g[(size_t)a * D0 + b] = g[(size_t)b * D0 + a] = s;
-            }
     }
     for (int a = 0; a < D; a++) {
         if (!zc[a]) continue;
@@ -186,7 +170,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
         }
     }
     DataMeta m{n, n, ds->n_nodes, ds->n_cols, D, ds->X, G.data(), ds->node_family, ds->node_col0, lfact.data(),
-               Gw.data(), gw_index.data(), D0, n_pois, pois_node.data()};
+               gw_index.data(), n_pois, pois_node.data()};
     Control c{ctrl->method, ctrl->max_iters, ctrl->solver, ctrl->nvars, ctrl->tol, ctrl->epsabs,
               ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale};
 

@@ -143,30 +143,6 @@ def test_partition_invariance_and_determinism():
     assert np.array_equal(np.concatenate([a["mlik"], b["mlik"]]), full["mlik"], equal_nan=True)
 
 
-def test_weighted_gram_is_symmetric_and_reproducible():
-    """The start values of the Poisson mle come from per-child weighted Gram matrices; their diagonal
-    tiles once held a write race between the (i, j) and (j, i) sums, which round differently."""
-    import ctypes as C
-    names, data, dists, mp, _ = synth.make_config(4, n=5000, n_nodes=8)
-    P = prep.prepare(data, dists, "mle")
-    pois = [i for i in range(len(names)) if P.node_family[i] == capi.POISSON]
-    D0 = 1 + P.X.shape[1]
-    L = capi.lib()
-    X = np.asarray(P.X)
-    Z = np.column_stack([np.ones(X.shape[0]), X])
-    ref = np.stack([Z.T @ ((X[:, P.node_col0[v]] + 0.1)[:, None] * Z) for v in pois])
-    first = None
-    for rep in range(3):
-        with abncache.DeviceData(P) as dd:
-            for k in range(4):
-                out = np.zeros((len(pois), D0, D0))
-                assert L.abn_b200_debug_gw(dd._h, out.ctypes.data_as(C.POINTER(C.c_double)), 1) == 0
-                first = out.copy() if first is None else first
-                assert np.array_equal(out, first)
-                assert np.array_equal(out, out.transpose(0, 2, 1))
-    assert H.rel_err(first, ref).max() < 1e-12
-
-
 def test_edge_cases():
     names, data, dists = synth.make_columns(64, ["gaussian", "binomial", "poisson"], seed=3)
     P = prep.prepare(data, dists, "mle")
