@@ -8,3 +8,6 @@ ncu --set full --clock-control none --import-source on --kernel-name-base demang
     -k 'regex:fit_kernel<\(int\)1, \(int\)4' -c 1 -o gpurun_out/prof_${TAG}_pois4 \
     python bench.py $A > gpurun_out/ncu_full_pois_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_full_pois_${TAG}.log
+# the binomial K=4 kernel alone (same command, other kernel filter):
+#   ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+#       -k 'regex:fit_kernel<\(int\)0, \(int\)4' -c 1 -o gpurun_out/prof_${TAG}_bin4 python bench.py $A
