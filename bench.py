@@ -170,7 +170,7 @@ def main():
         tot = sum(times)
         v = sample * len(times) / tot
         line = {
-            "impl": "reference", "metric": "score-cache GLM fits/sec", "value": v, "unit": "fits/s", "n_gpus": 0,
+            "impl": "reference", "metric": "score-cache GLM fits/sec", "value": v, "unit": "fits/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload},
@@ -179,7 +179,7 @@ def main():
                                        "CPU oracle (C restatement of the reference; the reference needs R+GSL+Armadillo)"},
             "e2e": {"value": v, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     # ------------------------------------------------------------------------------------------------
@@ -349,12 +349,26 @@ def main():
                                      "non_finite": int(status_counts[2])}},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line))
+    _emit(line)
     dev.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def _emit(line: dict) -> None:
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else that libraries write to
+    fd 1 (NCCL prints its version there) is sent to stderr, see _quiet_stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+def _quiet_stdout() -> int:
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
 if __name__ == "__main__":
+    _REAL_STDOUT = _quiet_stdout()
     sys.exit(main())
