@@ -5,7 +5,7 @@ synthetic 100 mixed Gaussian / binomial / Poisson nodes x 1 000 000 rows, max.pa
     python bench.py --gpus N --steps K --warmup W [--method mle|bayes] [--impl reference]
 
 A *step* is one pass of the hot path over one batch of the candidate list: `--batch` fits per GPU
-(default 65 536), taken as evenly spaced blocks of `--block` consecutive cache rows (default 512) out
+(default 262 144), taken as evenly spaced blocks of `--block` consecutive cache rows (default 512) out
 of the 16 180 000-row cache so that every step sees the cache's own mix of children / parent counts
 and its own neighbour structure (adjacent rows share the child and the leading parents). Every step
 uses different blocks; the data matrix (800 MB) is far larger than L2 (126 MB).
@@ -122,7 +122,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", default="mle", choices=["mle", "bayes"])
-    ap.add_argument("--batch", type=int, default=65536, help="fits per GPU per step")
+    ap.add_argument("--batch", type=int, default=262144, help="fits per GPU per step (1.6 % of config 4's cache)")
     ap.add_argument("--block", type=int, default=512)
     ap.add_argument("--rows", type=int, default=1_000_000, help="observations (BASELINE config: 1e6)")
     ap.add_argument("--nodes", type=int, default=100)
