@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("ABN_B200_LIB") or os.path.join(_HERE, "csrc", "libabn
 BINOMIAL, GAUSSIAN, POISSON, MULTINOMIAL = 1, 2, 3, 4
 METHOD_MLE, METHOD_BAYES = 0, 1
 SOLVER_NEWTON, SOLVER_HYBRID = 0, 1
+FLAG_EXACT_PATH = 1  # abn_control.flags: follow the reference's IRLS pass for pass (include/abn_b200.h)
 FIT_OK, FIT_NOT_CONVERGED, FIT_NON_FINITE = 0, 1, 2
 MAX_K = 32   # widest design
 FAST_K = 8   # widest design of the register-resident kernels
@@ -61,7 +62,7 @@ class Control(C.Structure):
         ("solver", C.c_int32),
         ("device", C.c_int32),
         ("nvars", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 

@@ -560,7 +560,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     CUDA_TRY(cudaEventRecord(ev[1], s));
 
     Control c{ctrl->method, ctrl->max_iters, ctrl->solver, ctrl->nvars, ctrl->tol, ctrl->epsabs,
-              ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale};
+              ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale, ctrl->flags};
     ResultPtrs rp{d->dRes, d->dRes + d->cap_rows, d->dRes + 2 * d->cap_rows, d->dRes + 3 * d->cap_rows, d->dStatus, d->dIters};
 
     const int tb = 128;

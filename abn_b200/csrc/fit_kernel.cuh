@@ -665,7 +665,7 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
                 mode = fit_consume(st, c, *acc);
                 st.passes--;
             }
-            if (KIND == RK_POIS && mode == PASS_PINIT) { // start values from the child's weighted Gram
+            if (KIND == RK_POIS && mode == PASS_PINIT && !(c.flags & 1)) { // Gram-only start; exact path: the reference's data pass
                 poisson_init_acc(m, d, ch, *acc);
                 mode = fit_consume(st, c, *acc);
                 st.passes--;

@@ -367,6 +367,7 @@ struct FitState {
     double xold[MAXM], dir[MAXM], cur_ll, step;
     double q_cur, q_prev, gd, dHd; // IRLS shortcuts: eta-scale length of the step in flight and of the one before; g'd, d'Hd
     int icpt;               // design column 0 is the constant 1 (H_00 = sum of the weights)
+    int shortcut;           // IRLS shortcuts enabled for this fit (off with ABN_FLAG_EXACT_PATH)
     int halvings;
     // Bayes: last accepted point, its residual f = grad g, Jacobian pieces
     double xc[MAXM], f[MAXM], dx[MAXM], diag[MAXM];
@@ -625,7 +626,8 @@ ABN_HDN int hy_after_iterate(FitState &s, const Control &c, int gsl_status)
 //                  gets a loglik pass; on acceptance the quadratic model is checked against the gain
 //                  it predicted (|gain - model| < 5 % of d'Hd/2), otherwise the point is redone in full.
 //
-// All of it needs an intercept column (H_00) and a contracting sequence (rho < 1); -DABN_SHORTCUT=0
+// All of it needs an intercept column (H_00) and a contracting sequence (rho < 1); ABN_FLAG_EXACT_PATH in
+// abn_control.flags (or -DABN_SHORTCUT=0)
 // restores the reference's pass-for-pass iteration. tests/test_host_sim.py and the GPU parity
 // tests hold both against the oracle, which iterates exactly like the reference.
 #ifndef ABN_SHORTCUT
@@ -654,7 +656,7 @@ ABN_HD double quad_form(const double *A, const double *d, int k)
 ABN_HD double eta_len(const FitState &s, double dHd)
 {
     const double h00 = s.J[0];
-    if (!ABN_SHORTCUT || !s.icpt || !(h00 > 0.0) || !(dHd >= 0.0) || !isfinite(dHd) || !isfinite(h00)) return -1.0;
+    if (!s.shortcut || !s.icpt || !(h00 > 0.0) || !(dHd >= 0.0) || !isfinite(dHd) || !isfinite(h00)) return -1.0;
     return sqrt(dHd / h00);
 }
 
@@ -666,6 +668,7 @@ ABN_HDN int fit_begin(FitState &s, const Control &c)
     s.loglik = s.aic = s.bic = NAN;
     s.loop_iter = 0; s.attempt = 0;
     s.q_cur = s.q_prev = 0.0; s.gd = s.dHd = 0.0;
+    s.shortcut = (ABN_SHORTCUT && !(c.flags & 1)) ? 1 : 0;
     if (c.method == MLE) {
         if (s.family == BINOMIAL) {
             for (int i = 0; i < s.k; i++) s.x[i] = 0.0; // x.zeros, irls_binomial_fast_br.cpp:19
@@ -779,7 +782,7 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
             pred_next = 3.0 * q * rho * rho;
         } else if (q >= 0.0) pred_next = q;
         s.q_cur = q;
-        s.have_ll = (pred_next < (ABN_SHORTCUT ? SC_FULL_Q : 1e-4)) || (nrm < 1e-4) || (s.iters + 1 >= c.max_iters);
+        s.have_ll = (pred_next < (s.shortcut ? SC_FULL_Q : 1e-4)) || (nrm < 1e-4) || (s.iters + 1 >= c.max_iters);
         return s.have_ll ? PASS_FULL : PASS_HG;
     }
     case PH_MLE_BIN_LL: {

@@ -7,6 +7,7 @@ namespace abnc {
 struct Control {
     int method, max_iters, solver, nvars;
     double tol, epsabs, prior_mean, prior_sd, gam_shape, gam_scale;
+    int flags; // ABN_FLAG_* of include/abn_b200.h
 };
 
 // device-resident description of the data set

@@ -113,6 +113,11 @@ typedef struct abn_candidates {
     const int32_t *parents; /* [rows * max_parents] 0-based node ids, -1 = unused slot      */
 } abn_candidates;
 
+/* abn_control.flags */
+#define ABN_FLAG_EXACT_PATH 1 /* mle: follow the reference's IRLS pass for pass - its own start values and its
+                                 own stopping rule - instead of ending a fit once the remaining terms are
+                                 below 1e-11 of |loglik| ("IRLS shortcuts"); ~2.5x the passes */
+
 /* build.control() scalars that reach the natives (R/build_score_cache.R:90-127,
  * R/build_score_cache_bayes.R:314-328) */
 typedef struct abn_control {
@@ -127,7 +132,7 @@ typedef struct abn_control {
     int32_t solver;     /* bayes: ABN_SOLVER_*                                               */
     int32_t device;     /* CUDA device ordinal this call runs on (one process per GPU)       */
     int32_t nvars;      /* MDL: number of variables in log(nvars), R/build_score_cache_mle.R:343 */
-    int32_t reserved;
+    int32_t flags;      /* ABN_FLAG_*; 0 by default                                          */
 } abn_control;
 
 /* Output arrays, all caller-allocated with `rows` entries; any pointer may be NULL.

@@ -54,6 +54,7 @@ SEXP abn_cuda_score_cache(SEXP R_X, SEXP R_family, SEXP R_col0, SEXP R_children,
     c.max_iters = (int) v[0]; c.tol = v[1]; c.epsabs = v[2]; c.prior_mean = v[3]; c.prior_sd = v[4];
     c.gam_shape = v[5]; c.gam_scale = v[6];
     c.nvars = asInteger(R_nvars); c.device = asInteger(R_device);
+    /* c.flags = ABN_FLAG_EXACT_PATH;   to follow the reference's IRLS pass for pass */
     const char *nm[] = { "mlik", "aic", "bic", "mdl", "error.code", "passes", "" };
     SEXP out = PROTECT(mkNamed(VECSXP, nm));
     for (int i = 0; i < 4; i++) SET_VECTOR_ELT(out, i, allocVector(REALSXP, rows));

@@ -172,7 +172,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
     DataMeta m{n, n, ds->n_nodes, ds->n_cols, D, ds->X, G.data(), ds->node_family, ds->node_col0, lfact.data(),
                gw_index.data(), n_pois, pois_node.data()};
     Control c{ctrl->method, ctrl->max_iters, ctrl->solver, ctrl->nvars, ctrl->tol, ctrl->epsabs,
-              ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale};
+              ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale, ctrl->flags};
 
 #pragma omp parallel for schedule(dynamic, 8)
     for (long long r = 0; r < cand->rows; r++) {
@@ -208,7 +208,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
                 mode = fit_consume(s, c, a);
                 s.passes--;
             }
-            if (c.method == MLE && d.family == POISSON && mode == PASS_PINIT) { // start values from Gw
+            if (c.method == MLE && d.family == POISSON && mode == PASS_PINIT && !(c.flags & 1)) { // Gram-only start values
                 poisson_init_acc(m, d, child, a);
                 mode = fit_consume(s, c, a);
                 s.passes--;

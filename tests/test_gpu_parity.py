@@ -143,6 +143,22 @@ def test_partition_invariance_and_determinism():
     assert np.array_equal(np.concatenate([a["mlik"], b["mlik"]]), full["mlik"], equal_nan=True)
 
 
+def test_exact_path_flag_matches_the_shortcut_path():
+    """ABN_FLAG_EXACT_PATH (the reference's pass-for-pass IRLS) and the default path agree far below the bar."""
+    names, data, dists, mp, _ = synth.make_config(4, n=20000, n_nodes=9)
+    d = len(names)
+    P = prep.prepare(data, dists, "mle")
+    ch0, par = abncache.enumerate_candidates(d, np.zeros((d, d), int), np.zeros((d, d), int), mp)
+    fast = H.gpu_score(P, ch0, par, H.control("mle", d))
+    exact = H.gpu_score(P, ch0, par, H.control("mle", d, **{"exact.path": True}))
+    ref = H.oracle_score(P, ch0, par, H.control("mle", d))
+    for k in ("mlik", "aic", "bic", "mdl"):
+        assert H.rel_err(exact[k], fast[k]).max() < 1e-10, k
+        assert H.rel_err(exact[k], ref[k]).max() < 1e-10, k
+    assert (exact["status"] == fast["status"]).all() and (exact["status"] == ref["status"]).all()
+    assert exact["iters"].sum() > 1.5 * fast["iters"].sum()
+
+
 def test_edge_cases():
     names, data, dists = synth.make_columns(64, ["gaussian", "binomial", "poisson"], seed=3)
     P = prep.prepare(data, dists, "mle")

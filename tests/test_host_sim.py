@@ -74,6 +74,29 @@ def test_mle_ex1_config1():
         assert (extra <= 0).all() and (extra <= -1).mean() > 0.5, f
 
 
+def test_mle_exact_path_flag_follows_the_reference_iteration_for_iteration():
+    """ABN_FLAG_EXACT_PATH: no IRLS shortcuts, the reference's own Poisson start (one data pass)."""
+    z, names, data, dists = _case("ex1_bayes.npz")
+    d = len(names)
+    P = prep.prepare(data, dists, "mle")
+    ch, nd = pyoracle.enumerate_mle(d, np.zeros((d, d), int), np.zeros((d, d), int), 3)
+    par = H.parents_from_node_defn(nd, 3)
+    exact = H.sim_score(P, ch.astype(np.int32), par, H.control("mle", d, **{"exact.path": True}))
+    fast = H.sim_score(P, ch.astype(np.int32), par, H.control("mle", d))
+    ref = H.oracle_score(P, ch.astype(np.int32), par, H.control("mle", d))
+    assert H.rel_err(exact["mlik"], ref["mlik"]).max() < 1e-10 and (exact["status"] == ref["status"]).all()
+    assert H.rel_err(exact["mlik"], fast["mlik"]).max() < 1e-10
+    fam = P.node_family[ch]
+    ok = ref["status"] == 0
+    # binomial: the reference's iterations minus the first one (Gram), plus at most one loglik-only pass
+    b = (fam == capi.BINOMIAL) & ok
+    extra = exact["iters"][b] - ref["iters"][b]
+    assert ((extra == -1) | (extra == 0)).all()
+    # Poisson: the start-value pass + one pass per IRLS trial; never fewer passes than the shortcut path
+    p = (fam == capi.POISSON) & ok
+    assert (exact["iters"][p] >= fast["iters"][p]).all() and exact["iters"][p].mean() > fast["iters"][p].mean() + 2
+
+
 def test_mle_rank_deficient_binomial_drops_leading_columns():
     """R/build_score_cache_mle.R:286-294 with a duplicated parent column."""
     rng = np.random.default_rng(5)
