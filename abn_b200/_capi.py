@@ -74,6 +74,9 @@ class Result(C.Structure):
         ("mdl", c_double_p),
         ("status", c_int32_p),
         ("iters", c_int32_p),
+        ("coef", c_double_p),
+        ("coef_stride", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -183,7 +186,9 @@ def make_candidates(child, parents):
     return cd, (ch, pa)
 
 
-def make_result(rows: int, method: int):
+def make_result(rows: int, method: int, coef_stride: int = 0):
+    """Result struct over fresh numpy arrays; coef_stride > 0 also asks for the coefficients
+    (rows x coef_stride, layout in include/abn_b200.h)."""
     arrs = {
         "mlik": np.full(rows, np.nan),
         "aic": np.full(rows, np.nan),
@@ -194,6 +199,10 @@ def make_result(rows: int, method: int):
     }
     res = Result(ptr_d(arrs["mlik"]), ptr_d(arrs["aic"]), ptr_d(arrs["bic"]), ptr_d(arrs["mdl"]),
                  ptr_i(arrs["status"]), ptr_i(arrs["iters"]))
+    if coef_stride > 0:
+        arrs["coef"] = np.full((rows, coef_stride), np.nan)
+        res.coef = ptr_d(arrs["coef"])
+        res.coef_stride = coef_stride
     return res, arrs
 
 

@@ -279,9 +279,10 @@ gauss_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ desc
     const int row = list[t];
     const FitDesc d = descs[row];
     if (c.method == MLE) {
-        double ll, aic, bic;
+        double ll, aic, bic, x[MAXM];
         int status;
-        gauss_mle_fit(m, d, &ll, &aic, &bic, &status);
+        gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x);
+        write_coef(out, row, d, x, d.k);
         if (out.mlik) out.mlik[row] = ll;
         if (out.aic) out.aic[row] = aic;
         if (out.bic) out.bic[row] = bic;
@@ -299,6 +300,7 @@ gauss_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ desc
     while (mode != PASS_DONE) mode = fit_consume(s, c, a);
     if (out.mlik) out.mlik[row] = s.loglik;
     if (out.status) out.status[row] = s.status;
+    write_coef(out, row, d, s.x, s.M);
     if (out.iters) out.iters[row] = 1;
 }
 
@@ -561,7 +563,15 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
 
     Control c{ctrl->method, ctrl->max_iters, ctrl->solver, ctrl->nvars, ctrl->tol, ctrl->epsabs,
               ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale, ctrl->flags};
-    ResultPtrs rp{d->dRes, d->dRes + d->cap_rows, d->dRes + 2 * d->cap_rows, d->dRes + 3 * d->cap_rows, d->dStatus, d->dIters};
+    double *dCoef = nullptr;
+    const int coef_stride = out->coef ? out->coef_stride : 0;
+    if (out->coef) {
+        if (coef_stride < 1) return fail(err, errlen, ABN_ERR_ARG, "coef_stride must be positive when coef is given");
+        CUDA_TRY(dev_alloc(&dCoef, (size_t)rows * coef_stride * sizeof(double), s));
+        CUDA_TRY(cudaMemsetAsync(dCoef, 0xff, (size_t)rows * coef_stride * sizeof(double), s)); // all-ones = NaN
+    }
+    ResultPtrs rp{d->dRes, d->dRes + d->cap_rows, d->dRes + 2 * d->cap_rows, d->dRes + 3 * d->cap_rows, d->dStatus, d->dIters,
+                  dCoef, coef_stride};
 
     const int tb = 128;
     resolve_kernel<<<(unsigned)((rows + tb - 1) / tb), tb, 0, s>>>(d->m, c.method, rows, width, d->dChild, d->dParents,
@@ -675,11 +685,13 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
         if (out->mdl) CUDA_TRY(cudaMemcpyAsync(out->mdl, rp.mdl, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     if (out->status) CUDA_TRY(cudaMemcpyAsync(out->status, rp.status, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (dCoef) CUDA_TRY(cudaMemcpyAsync(out->coef, dCoef, (size_t)rows * coef_stride * sizeof(double), cudaMemcpyDeviceToHost, s));
     std::vector<int> iters_host;
     int *iters_dst = out->iters;
     if (!iters_dst) { iters_host.resize(rows); iters_dst = iters_host.data(); }
     CUDA_TRY(cudaMemcpyAsync(iters_dst, rp.iters, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaEventRecord(ev[4], s));
+    dev_free(dCoef, s);
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
     tr.mark("score: upload + plan + fits + download");

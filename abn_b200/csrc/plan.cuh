@@ -29,7 +29,7 @@ struct FitDesc {
     short rank;           // rank of the full design as rank_cpp sees it
     short err;            // 1 = design wider than MAXK, 2 = child not supported
     short nlev;           // levels of a multinomial child (else 1)
-    short pad_;
+    short icpt0;          // the design had an intercept before rank handling
 };
 
 // kernel bucket of a resolved fit: the streaming kernels are instantiated per (row kind, k,
@@ -88,7 +88,7 @@ ABN_HDN void resolve_design(const DataMeta &m, int method, int child, const int 
     d.num_na = 0;
     d.err = 0;
     d.nlev = (short)(m.node_col0[child + 1] - m.node_col0[child]);
-    d.pad_ = 0;
+    d.icpt0 = 0;
     bool any_multi = false;
     int kdata = 0;
     for (int j = 0; j < width; j++) {
@@ -98,6 +98,7 @@ ABN_HDN void resolve_design(const DataMeta &m, int method, int child, const int 
         kdata += m.node_col0[p + 1] - m.node_col0[p];
     }
     bool icpt = (method == BAYES) || !any_multi; // _mle.R:266-270
+    d.icpt0 = icpt ? 1 : 0;
     int k = kdata + (icpt ? 1 : 0);
     d.kdata = (short)kdata;
     for (int j = 0; j < MAXK; j++) d.cols[j] = -1;
@@ -127,7 +128,8 @@ ABN_HDN void resolve_design(const DataMeta &m, int method, int child, const int 
 }
 
 // ---- Gaussian child, method = "mle": src/irls_gaussian_fast.cpp:34-49 from Gram blocks ---------
-ABN_HDN void gauss_mle_fit(const DataMeta &m, const FitDesc &d, double *loglik, double *aic, double *bic, int *status)
+ABN_HDN void gauss_mle_fit(const DataMeta &m, const FitDesc &d, double *loglik, double *aic, double *bic, int *status,
+                           double *coef = nullptr)
 {
     const int k = d.k;
     double A[MAXM * MAXM], S[MAXM * MAXM], b[MAXM], x[MAXM];
@@ -150,6 +152,8 @@ ABN_HDN void gauss_mle_fit(const DataMeta &m, const FitDesc &d, double *loglik, 
     *aic = -2 * ll + 2 * df;
     *bic = -2 * ll + log(n) * df;
     *status = (st < 0 || !isfinite(ll)) ? FIT_NON_FINITE : FIT_OK;
+    if (coef)
+        for (int i = 0; i < k; i++) coef[i] = x[i];
 }
 
 // ---- Bayes start values: beta0 = inv(X'X) X'y~ by LU, as generate_inits_n* do -------------------
@@ -265,6 +269,20 @@ ABN_HD void state_setup(const DataMeta &m, const FitDesc &d, int child, const Co
     s.n = (double)m.n;
     s.lfact = m.node_lfact[child];
     s.icpt = (d.k > 0 && d.cols[0] < 0) ? 1 : 0;
+}
+
+// Coefficient slots of a row of ResultPtrs::coef (abn_result.coef): slot 0 = intercept, slot 1 + t = the t-th
+// stored column of the parents in candidate order (a multinomial parent owns one slot per level column); for a
+// Gaussian child under method "bayes" the slot after the last column holds the precision. Columns the rank rule
+// dropped, absent intercepts and rows without coefficients (multinomial children, failed designs) stay NaN.
+ABN_HD void write_coef(const ResultPtrs &out, long long row, const FitDesc &d, const double *x, int M)
+{
+    if (!out.coef) return;
+    double *o = out.coef + row * out.coef_stride;
+    const int off = d.num_na + (d.icpt0 ? 0 : 1);
+    for (int j = 0; j < d.k; j++)
+        if (off + j < out.coef_stride) o[off + j] = x[j];
+    if (M > d.k && 1 + d.kdata < out.coef_stride) o[1 + d.kdata] = x[d.k];
 }
 
 // MDL of a scored mle row: bic + (1 + #selected stored columns - num.na) * log(nvars), _mle.R:343

@@ -755,7 +755,7 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
         if (converged || s.iters >= c.max_iters) {
             if (!converged) s.status = FIT_NOT_CONVERGED;
             if (s.have_ll) { mle_scores(s, a.ll, (double)k); return PASS_DONE; }
-            for (int i = 0; i < k; i++) s.x[i] = s.xold[i];
+            for (int i = 0; i < k; i++) { s.dir[i] = s.x[i]; s.x[i] = s.xold[i]; } // dir keeps the final coefficients
             s.phase = PH_MLE_BIN_LL;
             return PASS_LL;
         }
@@ -787,6 +787,7 @@ ABN_HDN int fit_consume(FitState &s, const Control &c, const PassAcc &a)
     }
     case PH_MLE_BIN_LL: {
         const int keep = s.status;
+        for (int i = 0; i < k; i++) s.x[i] = s.dir[i]; // the coefficients after the last update (returned ones)
         mle_scores(s, a.ll, (double)k);
         if (s.status == FIT_OK) s.status = keep;
         return PASS_DONE;

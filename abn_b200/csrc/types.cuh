@@ -29,6 +29,8 @@ struct DataMeta {
 struct ResultPtrs {
     double *mlik, *aic, *bic, *mdl;
     int *status, *iters;
+    double *coef;    // optional [rows x coef_stride]: fitted coefficients / posterior modes (plan.cuh write_coef)
+    int coef_stride;
 };
 
 } // namespace abnc

@@ -174,7 +174,8 @@ fit_wide_kernel(const DataMeta m, const Control c, const int *__restrict__ child
                 if (c.method == MLE) {
                     double ll, aic, bic;
                     int status;
-                    gauss_mle_fit(m, d, &ll, &aic, &bic, &status);
+                    gauss_mle_fit(m, d, &ll, &aic, &bic, &status, S.st.x);
+                    write_coef(out, row, d, S.st.x, d.k);
                     if (out.mlik) out.mlik[row] = ll;
                     if (out.aic) out.aic[row] = aic;
                     if (out.bic) out.bic[row] = bic;
@@ -188,6 +189,7 @@ fit_wide_kernel(const DataMeta m, const Control c, const int *__restrict__ child
                     while (md != PASS_DONE) md = fit_consume(S.st, c, S.acc);
                     if (out.mlik) out.mlik[row] = S.st.loglik;
                     if (out.status) out.status[row] = S.st.status;
+                    write_coef(out, row, d, S.st.x, S.st.M);
                 }
                 if (out.iters) out.iters[row] = 1;
             }
@@ -216,6 +218,7 @@ fit_wide_kernel(const DataMeta m, const Control c, const int *__restrict__ child
             }
             if (out.status) out.status[row] = S.st.status;
             if (out.iters) out.iters[row] = S.st.passes;
+            write_coef(out, row, d, S.st.x, S.st.M);
         }
         __syncwarp();
     }

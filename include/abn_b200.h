@@ -144,6 +144,18 @@ typedef struct abn_result {
     double *mdl;
     int32_t *status; /* ABN_FIT_*                                                            */
     int32_t *iters;  /* data passes / solver iterations executed, for the roofline account   */
+    /* Optional (NULL = not wanted): the fitted coefficients (mle: irls_*_cpp_fast()$coefficients; bayes: the
+     * posterior modes fit_single_node leaves in its `modes` vector, src/fit_single_node.c:182-194), rows x
+     * coef_stride, row-major. Slot 0 = intercept, slot 1 + t = the t-th stored column of the row's parents in
+     * candidate order (a multinomial parent owns one slot per level column); Gaussian child under bayes: the
+     * slot after the last column holds the precision parameter. Columns dropped by the rank rule, absent
+     * intercepts, multinomial children and failed designs are NaN. Slots >= coef_stride are not written. mle:
+     * the default path ends a fit once its SCORE is settled to 1e-11, which can leave coefficients ~1e-6 short
+     * along ill-conditioned directions; set ABN_FLAG_EXACT_PATH for the reference's own convergence (1e-8 step).
+     * This is the first step towards fitAbn. */
+    double *coef;
+    int32_t coef_stride;
+    int32_t reserved;
 } abn_result;
 
 typedef struct abn_data abn_data; /* opaque: device-resident data set + its global Gram     */

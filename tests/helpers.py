@@ -71,12 +71,12 @@ def sim_lib(wide=False):
     return _sim[key]
 
 
-def sim_score(P: prep.Prepared, children0, parents, ctrl, wide=False):
+def sim_score(P: prep.Prepared, children0, parents, ctrl, wide=False, coef_stride=0):
     """The product's solver state machines driven on the CPU (tests/host_sim.cpp); wide=True uses the
     MAXK = 32 build of the same headers (the limits of abn_b200/csrc/wide.cu)."""
     ds, k1 = capi.make_dataset(P.X, P.node_family, P.node_col0)
     cd, k2 = capi.make_candidates(children0, parents)
-    res, arrs = capi.make_result(cd.rows, ctrl.method)
+    res, arrs = capi.make_result(cd.rows, ctrl.method, coef_stride)
     buckets = np.zeros(max(1, cd.rows), dtype=np.intc)
     rc = sim_lib(wide).sim_score_cache(C.byref(ds), C.byref(cd), C.byref(ctrl), C.byref(res),
                                    buckets.ctypes.data_as(C.POINTER(C.c_int)))
@@ -90,12 +90,12 @@ def oracle_score(P: prep.Prepared, children0, parents, ctrl, threads=0):
     return pyoracle.score_cache(P.X, P.node_family, P.node_col0, children0, parents, ctrl, threads)
 
 
-def gpu_score(P: prep.Prepared, children0, parents, ctrl, device=0):
+def gpu_score(P: prep.Prepared, children0, parents, ctrl, device=0, coef_stride=0):
     """Through the C ABI: abn_b200_score_cache (one shot, host buffers in and out)."""
     L = capi.lib()
     ds, k1 = capi.make_dataset(P.X, P.node_family, P.node_col0)
     cd, k2 = capi.make_candidates(children0, parents)
-    res, arrs = capi.make_result(cd.rows, ctrl.method)
+    res, arrs = capi.make_result(cd.rows, ctrl.method, coef_stride)
     err = C.create_string_buffer(512)
     ctrl.device = device
     capi.check(L.abn_b200_score_cache(C.byref(ds), C.byref(cd), C.byref(ctrl), C.byref(res), err, len(err)), err)
@@ -116,3 +116,21 @@ def has_gpu():
         return capi.lib().abn_b200_device_count() > 0
     except Exception:
         return False
+
+
+def oracle_coef(P: prep.Prepared, child, parents_row, method="mle"):
+    """Coefficients of ONE fit from the oracle's single-fit entry points, in the slot layout of abn_result.coef
+    (intercept, then the parents' stored columns in candidate order). Binomial / Poisson / Gaussian children,
+    designs with an intercept."""
+    from oracle import pyoracle
+    X = np.asarray(P.X)
+    cols = [c for p in parents_row if p >= 0 for c in range(P.node_col0[p], P.node_col0[p + 1])]
+    D = np.column_stack([np.ones(X.shape[0])] + [X[:, c] for c in cols])
+    y = X[:, P.node_col0[child]]
+    fam = P.node_family[child]
+    if method == "mle":
+        f = {capi.GAUSSIAN: pyoracle.mle_gaussian, capi.BINOMIAL: pyoracle.mle_binomial_br,
+             capi.POISSON: pyoracle.mle_poisson}[fam](D, y)
+    else:
+        f = pyoracle.bayes_fit(fam, D, y, solver=capi.SOLVER_HYBRID)  # the reference's GSL hybrid path
+    return f

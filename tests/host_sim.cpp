@@ -182,6 +182,8 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
         if (buckets) buckets[r] = bucket_of(d);
         double ll = NAN, aic = NAN, bic = NAN, mdl = NAN;
         int status = FIT_NON_FINITE, passes = 0;
+        ResultPtrs rp{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out->coef, out->coef ? out->coef_stride : 0};
+        if (rp.coef) for (int j = 0; j < rp.coef_stride; j++) rp.coef[r * rp.coef_stride + j] = NAN;
         if (d.err || d.k == 0 || (d.family == MULTINOMIAL && (d.nlev < 2 || d.nlev > MN_MAXL || c.method != MLE || d.k > 8))) {
             // not supported by this build
         } else if (d.family == MULTINOMIAL) {
@@ -193,7 +195,9 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             while (more) { mn_pass(m, d, s.b, a); more = mn_consume(s, a); }
             ll = s.loglik; aic = s.aic; bic = s.bic; status = s.status; passes = s.passes;
         } else if (c.method == MLE && d.family == GAUSSIAN) {
-            gauss_mle_fit(m, d, &ll, &aic, &bic, &status);
+            double x[MAXM];
+            gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x);
+            write_coef(rp, r, d, x, d.k);
             passes = 1;
         } else {
             FitState s;
@@ -220,6 +224,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             }
             ll = s.loglik; aic = s.aic; bic = s.bic; status = s.status;
             passes = d.family == GAUSSIAN ? 1 : s.passes;
+            write_coef(rp, r, d, s.x, s.M);
         }
         if (c.method == MLE) mdl = mdl_of(bic, d, c.nvars);
         if (out->mlik) out->mlik[r] = ll;

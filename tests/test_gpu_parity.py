@@ -159,6 +159,39 @@ def test_exact_path_flag_matches_the_shortcut_path():
     assert exact["iters"].sum() > 1.5 * fast["iters"].sum()
 
 
+@pytest.mark.parametrize("method", ["mle", "bayes"])
+def test_coefficient_output(method):
+    """abn_result.coef through the C ABI against the oracle's single-fit entry points.
+    mle: the default path stops once the SCORE is settled (1e-11), which can leave the coefficients ~1e-6
+    short along ill-conditioned directions; ABN_FLAG_EXACT_PATH converges them like the reference."""
+    z, names, data, dists = _ex1()
+    d = len(names)
+    P = prep.prepare(data, dists, method)
+    ch0, par = abncache.enumerate_candidates(d, np.zeros((d, d), int), np.zeros((d, d), int), 3)
+    plain = H.gpu_score(P, ch0, par, H.control(method, d))
+    runs = [({}, 1e-4 if method == "mle" else 1e-7)]
+    if method == "mle":
+        runs.append(({"exact.path": True}, 1e-7))
+    for extra, tol in runs:
+        res = H.gpu_score(P, ch0, par, H.control(method, d, **extra), coef_stride=6)
+        if not extra:
+            assert np.array_equal(res["mlik"], plain["mlik"], equal_nan=True)  # asking for coefficients changes no score
+        rng = np.random.default_rng(5)
+        checked = 0
+        for i in rng.choice(len(ch0), 120, replace=False):
+            if res["status"][i] != 0:      # coefficients of flagged fits are whatever the last iterate was
+                continue
+            ref = H.oracle_coef(P, ch0[i], par[i], method)
+            if ref["status"] != 0:
+                continue
+            k = len(ref["coef"])
+            got = res["coef"][i]
+            assert np.isnan(got[k:]).all()
+            assert np.abs(got[:k] - ref["coef"]).max() < tol * (1 + np.abs(ref["coef"]).max()), (extra, i, got, ref["coef"])
+            checked += 1
+        assert checked > 80
+
+
 def test_edge_cases():
     names, data, dists = synth.make_columns(64, ["gaussian", "binomial", "poisson"], seed=3)
     P = prep.prepare(data, dists, "mle")

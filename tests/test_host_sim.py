@@ -235,3 +235,39 @@ def test_mle_shortcuts_on_small_and_strongly_dependent_data():
         pois = ok & (fam == capi.POISSON)
         assert sim["iters"][pois].mean() < ref["iters"][pois].mean()
     assert compared > 800 and worst < 1e-9, (compared, worst)
+
+
+@pytest.mark.parametrize("method", ["mle", "bayes"])
+def test_coefficient_output_matches_the_oracle(method):
+    """abn_result.coef (the first step towards fitAbn): coefficients / posterior modes per row."""
+    z, names, data, dists = _case("ex1_bayes.npz")
+    d = len(names)
+    P = prep.prepare(data, dists, method)
+    rng = np.random.default_rng(11)
+    rows = []
+    for ch in range(d):
+        others = [j for j in range(d) if j != ch]
+        for k in (0, 1, 3):
+            rows.append((ch, sorted(rng.choice(others, k, replace=False).tolist()) + [-1] * (3 - k)))
+    ch = np.array([r[0] for r in rows], np.int32)
+    par = np.array([r[1] for r in rows], np.int32)
+    for extra in ({}, {"exact.path": True}):
+        sim = H.sim_score(P, ch, par, H.control(method, d, **extra), coef_stride=6)
+        checked = 0
+        for i in range(len(ch)):
+            if sim["status"][i] != 0:
+                continue
+            ref = H.oracle_coef(P, ch[i], par[i], method)
+            if ref["status"] != 0:
+                continue
+            k = len(ref["coef"])                       # intercept + parents (+ precision: Gaussian child, bayes)
+            nb = 1 + int((par[i] >= 0).sum())          # all nodes of ex1 own one column
+            got = sim["coef"][i]
+            assert np.isnan(got[k:]).all()
+            if k > nb:                                 # the precision sits in the slot after the last column
+                assert abs(got[nb] - ref["coef"][nb]) < 1e-7 * (1 + abs(ref["coef"][nb]))
+            # mle: coefficients to 1e-7 absolute (the shortcut path stops ~1e-8 short in the eta scale), 1e-9 exact path
+            tol = 1e-6 if (method == "mle" and not extra) else 1e-7
+            assert np.abs(got[:nb] - ref["coef"][:nb]).max() < tol * (1 + np.abs(ref["coef"][:nb]).max()), (i, got, ref["coef"])
+            checked += 1
+        assert checked > 20
