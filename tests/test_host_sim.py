@@ -271,3 +271,28 @@ def test_coefficient_output_matches_the_oracle(method):
             assert np.abs(got[:nb] - ref["coef"][:nb]).max() < tol * (1 + np.abs(ref["coef"][:nb]).max()), (i, got, ref["coef"])
             checked += 1
         assert checked > 20
+
+
+def test_coefficient_slots_with_dropped_columns_and_without_intercept():
+    """Slot layout of abn_result.coef when the design is not [1 | parents]: the binomial rank rule drops LEADING
+    columns (R/build_score_cache_mle.R:286-294) and a multinomial parent removes the intercept (:266-270)."""
+    rng = np.random.default_rng(5)
+    n = 400
+    g = rng.normal(size=n)
+    codes = rng.integers(1, 4, size=n)
+    data = {"b": (rng.random(n) < 1 / (1 + np.exp(-g))).astype(float), "g1": g, "g2": g.copy(),
+            "g3": rng.normal(size=n), "m": (codes, ["x", "y", "z"])}
+    dists = {"b": "binomial", "g1": "gaussian", "g2": "gaussian", "g3": "gaussian", "m": "multinomial"}
+    P = prep.prepare(data, dists, "mle")
+    ch0 = np.zeros(3, np.int32)
+    par = np.array([[1, 2, -1], [1, 3, -1], [3, 4, -1]], np.int32)
+    sim = H.sim_score(P, ch0, par, H.control("mle", 5, **{"exact.path": True}), coef_stride=8)
+    c = sim["coef"]
+    # row 0: [1 | g1 | g2] with g1 == g2 is rank 2: leading columns go until the rest has full rank
+    assert np.isnan(c[0][0]) and np.isfinite(c[0][2]) and np.isnan(c[0][3:]).all()
+    # row 1: full rank with an intercept: slots 0, 1, 2
+    assert np.isfinite(c[1][:3]).all() and np.isnan(c[1][3:]).all()
+    ref = H.oracle_coef(P, 0, par[1], "mle")
+    assert np.abs(c[1][:3] - ref["coef"]).max() < 1e-7
+    # row 2: multinomial parent -> no intercept: slot 0 stays NaN, g3 in slot 1, the three level columns after it
+    assert np.isnan(c[2][0]) and np.isfinite(c[2][1:5]).all() and np.isnan(c[2][5:]).all()
