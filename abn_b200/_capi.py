@@ -18,6 +18,7 @@ BINOMIAL, GAUSSIAN, POISSON, MULTINOMIAL = 1, 2, 3, 4
 METHOD_MLE, METHOD_BAYES = 0, 1
 SOLVER_NEWTON, SOLVER_HYBRID = 0, 1
 FLAG_EXACT_PATH = 1  # abn_control.flags: follow the reference's IRLS pass for pass (include/abn_b200.h)
+FLAG_NO_BIAS_REDUCTION = 2  # binomial mle without the bias reduction (irls_binomial_cpp_fast, fitAbn's first choice)
 FIT_OK, FIT_NOT_CONVERGED, FIT_NON_FINITE = 0, 1, 2
 MAX_K = 32   # widest design
 FAST_K = 8   # widest design of the register-resident kernels

@@ -48,7 +48,7 @@ _DEFAULTS = {
     "seed": 9062019,
 }
 # extra, B200-specific knobs carried in the same control list
-_EXTRA_DEFAULTS = {"solver": "hybrid", "device": 0, "exact.path": False}
+_EXTRA_DEFAULTS = {"solver": "hybrid", "device": 0, "exact.path": False, "bias.reduction": True}
 
 
 def build_control(method: str = "bayes", **kwargs) -> dict:
@@ -94,6 +94,11 @@ def _check_control(control, method):
     return base
 
 
+def _flags(ctrl: dict) -> int:
+    return ((capi.FLAG_EXACT_PATH if ctrl.get("exact.path", False) else 0)
+            | (0 if ctrl.get("bias.reduction", True) else capi.FLAG_NO_BIAS_REDUCTION))
+
+
 def to_c_control(ctrl: dict, method: str, nvars: int) -> capi.Control:
     solver = ctrl.get("solver", "hybrid")
     solver_code = {"hybrid": capi.SOLVER_HYBRID, "newton": capi.SOLVER_NEWTON}.get(solver, solver)
@@ -103,12 +108,12 @@ def to_c_control(ctrl: dict, method: str, nvars: int) -> capi.Control:
             prior_mean=float(ctrl["mean"]), prior_sd=1.0 / np.sqrt(float(ctrl["prec"])),      # _bayes.R:314
             gam_shape=float(ctrl["loggam.shape"]), gam_scale=1.0 / float(ctrl["loggam.inv.scale"]),  # _bayes.R:315
             solver=int(solver_code), device=int(ctrl.get("device", 0)), nvars=int(nvars),
-            flags=capi.FLAG_EXACT_PATH if ctrl.get("exact.path", False) else 0)
+            flags=_flags(ctrl))
     return capi.Control(
         method=capi.METHOD_MLE, max_iters=int(ctrl["max.iters"]), tol=float(ctrl["tol"]), epsabs=1e-7,
         prior_mean=0.0, prior_sd=1.0, gam_shape=1.0, gam_scale=1.0, solver=int(solver_code),
         device=int(ctrl.get("device", 0)), nvars=int(nvars),
-        flags=capi.FLAG_EXACT_PATH if ctrl.get("exact.path", False) else 0)
+        flags=_flags(ctrl))
 
 
 # ---- dag.banned / dag.retained ---------------------------------------------------------------------

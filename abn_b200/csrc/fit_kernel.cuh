@@ -645,7 +645,7 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
             cp[j] = m.X + (long long)(col < 0 ? 0 : col) * m.ld;
         }
         const double *y = m.X + (long long)d.ycol * m.ld;
-        const RowConst rc = make_row_const(K, (double)m.n, exp_tab, log_tab, KIND == RK_POIS ? lnmu_tab : nullptr);
+        const RowConst rc = make_row_const((c.flags & 2) ? 0 : K, (double)m.n, exp_tab, log_tab, KIND == RK_POIS ? lnmu_tab : nullptr);
 
         int mode = 0;
         if (lane == 0) {
@@ -660,7 +660,7 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
             if (c.method == BAYES) bayes_inits(m, d, ch, st);
             mode = fit_begin(st, c);
             if (KIND == RK_BIN_MLE) { // iteration 1 from the Gram matrix, no data pass
-                binomial_first_acc(m, d, *acc);
+                binomial_first_acc(m, d, *acc, !(c.flags & 2));
                 st.have_ll = 1;
                 mode = fit_consume(st, c, *acc);
                 st.passes--;

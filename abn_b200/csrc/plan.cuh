@@ -218,10 +218,10 @@ ABN_HD void gauss_gram_acc(const DataMeta &m, const FitDesc &d, PassAcc &a)
 // rho = g'/(g (1 - g)) = 1 exactly, W = 1/4 and W z = b' - 1/2 with b' = bp0 + y (bp1 - bp0):
 //   X'WX = X'X / 4,   X'[rho (b' - g)] = (bp0 - 1/2) X'1 + (bp1 - bp0) X'y
 // - all entries of the global Gram, so the first of the ~4-8 data passes of a fit is free.
-ABN_HD void binomial_first_acc(const DataMeta &m, const FitDesc &d, PassAcc &a)
+ABN_HD void binomial_first_acc(const DataMeta &m, const FitDesc &d, PassAcc &a, bool bias_reduction = true)
 {
     const int k = d.k;
-    const double dfn = (double)k / (double)m.n;
+    const double dfn = bias_reduction ? (double)k / (double)m.n : 0.0;
     const double bp0 = (0.0 + dfn * 0.5) / (1 + dfn), bp1 = (1.0 + dfn * 0.5) / (1 + dfn);
     const long long gy = gram_col(d.ycol);
     for (int i = 0; i < k; i++) {

@@ -27,7 +27,8 @@ struct RowConst {
     const double *logtab; // fast_log_ge1 table
 };
 
-// b' = (y + 0.5 k/n) / (1 + k/n), irls_binomial_fast_br.cpp:58
+// b' = (y + 0.5 k/n) / (1 + k/n), irls_binomial_fast_br.cpp:58; callers pass k = 0 for the plain b' = y of
+// irls_binomial_fast.cpp (ABN_FLAG_NO_BIAS_REDUCTION)
 ABN_HD RowConst make_row_const(int k, double n, const double *tab, const double *logtab, const double *lnmu = nullptr)
 {
     RowConst c;

@@ -53,7 +53,7 @@ __device__ void wide_pass(const DataMeta &m, const Control &c, WideShared &S, in
     const int npairs = k * (k + 1) / 2;
     const bool pinit = (mode == PASS_PINIT);
     const int kind = pinit ? RK_PINIT : (d.family == POISSON ? RK_POIS : (c.method == MLE ? RK_BIN_MLE : RK_BIN_BAYES));
-    const RowConst rc = make_row_const(k, (double)m.n, S.exp_tab, S.log_tab, nullptr);
+    const RowConst rc = make_row_const((c.flags & 2) ? 0 : k, (double)m.n, S.exp_tab, S.log_tab, nullptr);
     const double *y = m.X + (long long)d.ycol * m.ld;
 
     double hacc[PPL];

@@ -118,6 +118,10 @@ typedef struct abn_candidates {
                                  own stopping rule - instead of ending a fit once the remaining terms are
                                  below 1e-11 of |loglik| ("IRLS shortcuts"); ~2.5x the passes */
 
+#define ABN_FLAG_NO_BIAS_REDUCTION 2 /* mle, binomial children: b' = y, i.e. irls_binomial_cpp_fast (src/irls_binomial_fast.cpp)
+                                        instead of the bias-reduced irls_binomial_cpp_fast_br the score cache uses
+                                        (fitAbn's first choice, R/fitabn_mle.R:585) */
+
 /* build.control() scalars that reach the natives (R/build_score_cache.R:90-127,
  * R/build_score_cache_bayes.R:314-328) */
 typedef struct abn_control {

@@ -60,6 +60,8 @@ typedef struct or_fit {
 void or_mle_gaussian(const double *X, const double *y, long n, int k, or_fit *out);   /* src/irls_gaussian_fast.cpp:12-99 */
 void or_mle_binomial_br(const double *X, const double *y, long n, int k, int maxit, double tol,
                         or_fit *out);                                                 /* src/irls_binomial_fast_br.cpp:15-153 */
+void or_mle_binomial(const double *X, const double *y, long n, int k, int maxit, double tol,
+                     or_fit *out);                                                    /* src/irls_binomial_fast.cpp:14-150 */
 void or_mle_poisson(const double *X, const double *y, long n, int k, int maxit, double tol,
                     or_fit *out);                                                     /* src/irls_poisson_fast.cpp:16-160 */
 /* nnet.default(x=X, y=onehot, mask, size=0, skip=TRUE, softmax=TRUE, rang=0) + BFGS (vmmin),

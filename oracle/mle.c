@@ -71,8 +71,10 @@ void or_mle_gaussian(const double *X, const double *y, long n, int k, or_fit *ou
 }
 
 /* ------------------------------------------------------------------------------------------ */
-void or_mle_binomial_br(const double *X, const double *y, long n, int k, int maxit, double tol,
-                        or_fit *out)
+/* both binomial IRLS variants of the reference: src/irls_binomial_fast_br.cpp (br = 1, line numbers below)
+ * and src/irls_binomial_fast.cpp (br = 0: the same loop with b' = b, :47-76, loglik :89) */
+static void mle_binomial_any(const double *X, const double *y, long n, int k, int maxit, double tol, int br,
+                             or_fit *out)
 {
     memset(out, 0, sizeof(*out));
     double x[OR_MAXM] = {0}, xold[OR_MAXM], G[OR_MAXM * OR_MAXM], rhs[OR_MAXM];
@@ -86,7 +88,7 @@ void or_mle_binomial_br(const double *X, const double *y, long n, int k, int max
             double e = exp(-1.0 * eta[j]);                    /* :54 */
             double g = 1.0 / (1.0 + e);                       /* :55 */
             double gprime = e / ((1.0 + e) * (1.0 + e));      /* :56 */
-            double bprime = (y[j] + (df / nobs) * (0.5)) / (1 + (df / nobs)); /* :58 */
+            double bprime = br ? (y[j] + (df / nobs) * (0.5)) / (1 + (df / nobs)) : y[j]; /* :58 */
             z[j] = eta[j] + (bprime - g) / gprime;            /* :63 */
             W[j] = (gprime * gprime) / (g * (1.0 - g));       /* :65-66 */
         }
@@ -114,6 +116,17 @@ void or_mle_binomial_br(const double *X, const double *y, long n, int k, int max
                   : (converged ? ABN_FIT_OK : ABN_FIT_NOT_CONVERGED);
     memcpy(out->coef, x, sizeof(double) * k);
     free(eta); free(W); free(z);
+}
+
+void or_mle_binomial_br(const double *X, const double *y, long n, int k, int maxit, double tol, or_fit *out)
+{
+    mle_binomial_any(X, y, n, k, maxit, tol, 1, out);
+}
+
+/* src/irls_binomial_fast.cpp:14-150 - what fitAbn(method = "mle") tries first (R/fitabn_mle.R:585) */
+void or_mle_binomial(const double *X, const double *y, long n, int k, int maxit, double tol, or_fit *out)
+{
+    mle_binomial_any(X, y, n, k, maxit, tol, 0, out);
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -57,6 +57,7 @@ def lib() -> C.CDLL:
     fp = C.POINTER(Fit)
     L.or_mle_gaussian.argtypes = [dp, dp, C.c_long, C.c_int, fp]
     L.or_mle_binomial_br.argtypes = [dp, dp, C.c_long, C.c_int, C.c_int, C.c_double, fp]
+    L.or_mle_binomial.argtypes = [dp, dp, C.c_long, C.c_int, C.c_int, C.c_double, fp]
     L.or_mle_poisson.argtypes = [dp, dp, C.c_long, C.c_int, C.c_int, C.c_double, fp]
     L.or_mle_multinomial.argtypes = [dp, ip, C.c_long, C.c_int, C.c_int, C.c_int, fp]
     L.or_rank_cpp.argtypes = [dp, C.c_long, C.c_int]
@@ -128,6 +129,14 @@ def mle_binomial_br(X, y, maxit=100, tol=1e-8):
     Xf, yy = _xy(X, y)
     f = Fit()
     lib().or_mle_binomial_br(_dp(Xf), _dp(yy), Xf.shape[0], Xf.shape[1], maxit, tol, C.byref(f))
+    return _fit_dict(f, Xf.shape[1])
+
+
+def mle_binomial(X, y, maxit=100, tol=1e-8):
+    """irls_binomial_cpp_fast: no bias reduction (fitAbn's first choice)."""
+    Xf, yy = _xy(X, y)
+    f = Fit()
+    lib().or_mle_binomial(_dp(Xf), _dp(yy), Xf.shape[0], Xf.shape[1], maxit, tol, C.byref(f))
     return _fit_dict(f, Xf.shape[1])
 
 

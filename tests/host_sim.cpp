@@ -29,11 +29,11 @@ const double *host_log_table()
 }
 
 template <int KIND>
-void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode, PassAcc &a)
+void host_pass(const DataMeta &m, const FitDesc &d, const double *beta, int mode, PassAcc &a, bool bias_reduction = true)
 {
     const int k = d.k;
     std::memset(&a, 0, sizeof(a));
-    RowConst rc = make_row_const(k, (double)m.n, h_exp2_table, host_log_table());
+    RowConst rc = make_row_const(bias_reduction ? k : 0, (double)m.n, h_exp2_table, host_log_table());
     const double *y = m.X + (size_t)d.ycol * m.ld;
     const bool need_h = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_HESS);
     const bool need_g = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_GRAD);
@@ -76,7 +76,7 @@ void run_pass(const DataMeta &m, const FitDesc &d, const Control &c, const FitSt
 #endif
     if (mode == PASS_PINIT) { host_pass<RK_PINIT>(m, d, s.x, PASS_HG, a); return; }
     if (d.family == POISSON) { host_pass<RK_POIS>(m, d, s.x, mode, a); return; }
-    if (c.method == MLE) host_pass<RK_BIN_MLE>(m, d, s.x, mode, a);
+    if (c.method == MLE) host_pass<RK_BIN_MLE>(m, d, s.x, mode, a, !(c.flags & 2));
     else host_pass<RK_BIN_BAYES>(m, d, s.x, mode, a);
 }
 
@@ -207,7 +207,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             PassAcc a;
             int mode = fit_begin(s, c);
             if (c.method == MLE && d.family == BINOMIAL) { // as fit_kernel: iteration 1 from the Gram matrix
-                binomial_first_acc(m, d, a);
+                binomial_first_acc(m, d, a, !(c.flags & 2));
                 s.have_ll = 1;
                 mode = fit_consume(s, c, a);
                 s.passes--;

@@ -192,6 +192,35 @@ def test_coefficient_output(method):
         assert checked > 80
 
 
+def test_binomial_without_bias_reduction():
+    """ABN_FLAG_NO_BIAS_REDUCTION through the C ABI: irls_binomial_cpp_fast, fitAbn's first choice."""
+    from oracle import pyoracle
+    z, names, data, dists = _ex1()
+    d = len(names)
+    P = prep.prepare(data, dists, "mle")
+    X = np.asarray(P.X)
+    kids = [i for i in range(d) if P.node_family[i] == capi.BINOMIAL]
+    rng = np.random.default_rng(3)
+    rows = []
+    for ch in kids:
+        others = [j for j in range(d) if j != ch and P.node_family[j] != capi.POISSON]
+        for k in (1, 2, 3):
+            rows.append((ch, sorted(rng.choice(others, k, replace=False).tolist()) + [-1] * (3 - k)))
+    ch = np.array([r[0] for r in rows], np.int32)
+    par = np.array([r[1] for r in rows], np.int32)
+    res = H.gpu_score(P, ch, par, H.control("mle", d, **{"bias.reduction": False, "exact.path": True}), coef_stride=5)
+    fast = H.gpu_score(P, ch, par, H.control("mle", d, **{"bias.reduction": False}))
+    for i in range(len(ch)):
+        cols = [P.node_col0[p] for p in par[i] if p >= 0]
+        D = np.column_stack([np.ones(X.shape[0])] + [X[:, c] for c in cols])
+        ref = pyoracle.mle_binomial(D, X[:, P.node_col0[ch[i]]])
+        k = D.shape[1]
+        assert res["status"][i] == 0 and ref["status"] == 0
+        assert np.abs(res["coef"][i][:k] - ref["coef"]).max() < 1e-7 * (1 + np.abs(ref["coef"]).max())
+        assert abs(res["mlik"][i] - ref["loglik"]) < 1e-10 * abs(ref["loglik"])
+        assert abs(fast["mlik"][i] - ref["loglik"]) < 1e-10 * abs(ref["loglik"])
+
+
 def test_edge_cases():
     names, data, dists = synth.make_columns(64, ["gaussian", "binomial", "poisson"], seed=3)
     P = prep.prepare(data, dists, "mle")

@@ -296,3 +296,47 @@ def test_coefficient_slots_with_dropped_columns_and_without_intercept():
     assert np.abs(c[1][:3] - ref["coef"]).max() < 1e-7
     # row 2: multinomial parent -> no intercept: slot 0 stays NaN, g3 in slot 1, the three level columns after it
     assert np.isnan(c[2][0]) and np.isfinite(c[2][1:5]).all() and np.isnan(c[2][5:]).all()
+
+
+def test_binomial_mle_without_bias_reduction_is_plain_logistic_regression():
+    """ABN_FLAG_NO_BIAS_REDUCTION = irls_binomial_cpp_fast (src/irls_binomial_fast.cpp), what fitAbn(method = "mle")
+    tries first: the oracle's restatement equals an independent Newton-Raphson logistic MLE (the reference's own
+    test compares it with glm(), tests/testthat/test-fitabn_mle.R:114-130), and the product's state machines
+    match the oracle in score and coefficients."""
+    z, names, data, dists = _case("ex1_bayes.npz")
+    d = len(names)
+    P = prep.prepare(data, dists, "mle")
+    X = np.asarray(P.X)
+    kids = [i for i in range(d) if P.node_family[i] == capi.BINOMIAL]
+    rng = np.random.default_rng(3)
+    rows = []
+    for ch in kids:
+        others = [j for j in range(d) if j != ch and P.node_family[j] != capi.POISSON]  # unscaled counts separate b1
+        for k in (1, 2, 3):
+            rows.append((ch, sorted(rng.choice(others, k, replace=False).tolist()) + [-1] * (3 - k)))
+    ch = np.array([r[0] for r in rows], np.int32)
+    par = np.array([r[1] for r in rows], np.int32)
+    ctrl = H.control("mle", d, **{"bias.reduction": False, "exact.path": True})
+    sim = H.sim_score(P, ch, par, ctrl, coef_stride=5)
+    fast = H.sim_score(P, ch, par, H.control("mle", d, **{"bias.reduction": False}))
+    for i in range(len(ch)):
+        cols = [P.node_col0[p] for p in par[i] if p >= 0]
+        D = np.column_stack([np.ones(X.shape[0])] + [X[:, c] for c in cols])
+        y = X[:, P.node_col0[ch[i]]]
+        ref = pyoracle.mle_binomial(D, y)
+        assert ref["status"] == 0 and sim["status"][i] == 0
+        b = np.zeros(D.shape[1])                      # independent Newton-Raphson on the plain likelihood
+        for _ in range(50):
+            p = 1 / (1 + np.exp(-D @ b))
+            step = np.linalg.solve(D.T @ ((p * (1 - p))[:, None] * D), D.T @ (y - p))
+            b += step
+            if np.abs(step).max() < 1e-13:
+                break
+        assert np.abs(ref["coef"] - b).max() < 1e-8 * (1 + np.abs(b).max())
+        k = D.shape[1]
+        assert np.abs(sim["coef"][i][:k] - ref["coef"]).max() < 1e-7 * (1 + np.abs(b).max())
+        assert abs(sim["mlik"][i] - ref["loglik"]) < 1e-10 * abs(ref["loglik"])
+        assert abs(fast["mlik"][i] - ref["loglik"]) < 1e-10 * abs(ref["loglik"])
+    # and it is a different estimator from the bias-reduced one the cache uses
+    br = H.sim_score(P, ch, par, H.control("mle", d))
+    assert np.abs(br["mlik"] - sim["mlik"]).max() > 1e-6
