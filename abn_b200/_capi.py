@@ -78,6 +78,7 @@ class Result(C.Structure):
         ("coef", c_double_p),
         ("coef_stride", C.c_int32),
         ("reserved", C.c_int32),
+        ("se", c_double_p),
     ]
 
 
@@ -187,7 +188,7 @@ def make_candidates(child, parents):
     return cd, (ch, pa)
 
 
-def make_result(rows: int, method: int, coef_stride: int = 0):
+def make_result(rows: int, method: int, coef_stride: int = 0, se: bool = False):
     """Result struct over fresh numpy arrays; coef_stride > 0 also asks for the coefficients
     (rows x coef_stride, layout in include/abn_b200.h)."""
     arrs = {
@@ -204,6 +205,9 @@ def make_result(rows: int, method: int, coef_stride: int = 0):
         arrs["coef"] = np.full((rows, coef_stride), np.nan)
         res.coef = ptr_d(arrs["coef"])
         res.coef_stride = coef_stride
+        if se:
+            arrs["se"] = np.full((rows, coef_stride), np.nan)
+            res.se = ptr_d(arrs["se"])
     return res, arrs
 
 

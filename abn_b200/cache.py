@@ -241,11 +241,12 @@ class DeviceData:
         err = C.create_string_buffer(512)
         capi.check(L.abn_b200_data_create(C.byref(self._ds), device, C.byref(self._h), err, len(err)), err)
 
-    def score(self, children0, parents, control: capi.Control, coef_stride: int = 0) -> dict:
-        """coef_stride > 0 also returns ``coef`` (rows x coef_stride; slot layout in include/abn_b200.h)."""
+    def score(self, children0, parents, control: capi.Control, coef_stride: int = 0, se: bool = False) -> dict:
+        """coef_stride > 0 also returns ``coef`` (rows x coef_stride; slot layout in include/abn_b200.h), and
+        with se=True the mle standard errors in the same layout."""
         L = capi.lib()
         cd, keep = capi.make_candidates(children0, parents)
-        res, arrs = capi.make_result(cd.rows, control.method, coef_stride)
+        res, arrs = capi.make_result(cd.rows, control.method, coef_stride, se)
         err = C.create_string_buffer(512)
         capi.check(L.abn_b200_score(self._h, C.byref(cd), C.byref(control), C.byref(res), err, len(err)), err)
         del keep

@@ -279,10 +279,11 @@ gauss_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ desc
     const int row = list[t];
     const FitDesc d = descs[row];
     if (c.method == MLE) {
-        double ll, aic, bic, x[MAXM];
+        double ll, aic, bic, x[MAXM], se[MAXM];
         int status;
-        gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x);
+        gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x, out.se ? se : nullptr);
         write_coef(out, row, d, x, d.k);
+        if (out.se) { ResultPtrs o = out; o.coef = out.se; write_coef(o, row, d, se, d.k); }
         if (out.mlik) out.mlik[row] = ll;
         if (out.aic) out.aic[row] = aic;
         if (out.bic) out.bic[row] = bic;
@@ -570,8 +571,14 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
         CUDA_TRY(dev_alloc(&dCoef, (size_t)rows * coef_stride * sizeof(double), s));
         CUDA_TRY(cudaMemsetAsync(dCoef, 0xff, (size_t)rows * coef_stride * sizeof(double), s)); // all-ones = NaN
     }
+    double *dSe = nullptr;
+    if (out->se) {
+        if (!out->coef) return fail(err, errlen, ABN_ERR_ARG, "se needs coef (they share coef_stride)");
+        CUDA_TRY(dev_alloc(&dSe, (size_t)rows * coef_stride * sizeof(double), s));
+        CUDA_TRY(cudaMemsetAsync(dSe, 0xff, (size_t)rows * coef_stride * sizeof(double), s));
+    }
     ResultPtrs rp{d->dRes, d->dRes + d->cap_rows, d->dRes + 2 * d->cap_rows, d->dRes + 3 * d->cap_rows, d->dStatus, d->dIters,
-                  dCoef, coef_stride};
+                  dCoef, coef_stride, dSe};
 
     const int tb = 128;
     resolve_kernel<<<(unsigned)((rows + tb - 1) / tb), tb, 0, s>>>(d->m, c.method, rows, width, d->dChild, d->dParents,
@@ -686,12 +693,14 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     }
     if (out->status) CUDA_TRY(cudaMemcpyAsync(out->status, rp.status, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (dCoef) CUDA_TRY(cudaMemcpyAsync(out->coef, dCoef, (size_t)rows * coef_stride * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dSe) CUDA_TRY(cudaMemcpyAsync(out->se, dSe, (size_t)rows * coef_stride * sizeof(double), cudaMemcpyDeviceToHost, s));
     std::vector<int> iters_host;
     int *iters_dst = out->iters;
     if (!iters_dst) { iters_host.resize(rows); iters_dst = iters_host.data(); }
     CUDA_TRY(cudaMemcpyAsync(iters_dst, rp.iters, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaEventRecord(ev[4], s));
     dev_free(dCoef, s);
+    dev_free(dSe, s);
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
     tr.mark("score: upload + plan + fits + download");

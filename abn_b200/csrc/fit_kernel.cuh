@@ -696,6 +696,7 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
             if (out.status) out.status[row] = st.status;
             if (out.iters) out.iters[row] = st.passes;
             write_coef(out, row, d, st.x, st.M);
+            write_se(out, row, d, st, c.method);
         }
         __syncwarp();
     }

@@ -127,9 +127,28 @@ ABN_HDN void resolve_design(const DataMeta &m, int method, int child, const int 
     }
 }
 
+// Standard errors as fitAbn(method = "mle") derives them from the `varcov` its IRLS functions return
+// (R/fitabn_mle.R:715-745): se_i = sqrt(scale * inv(V)_ii) with V = X'WX of the last iteration (binomial,
+// Poisson; scale = 1) or X'X (Gaussian; scale = mse = sse / (n - k)). V is MAXM-strided; NaN if singular.
+ABN_HDN void se_from_information(const double *V, int k, double scale, double *se)
+{
+    double LU[MAXM * MAXM], e[MAXM], col[MAXM];
+    int perm[MAXM];
+    for (int i = 0; i < k; i++)
+        for (int j = 0; j < k; j++) A_(LU, i, j) = A_(const_cast<double *>(V), i, j);
+    lu_decomp(LU, k, perm);
+    const bool bad = lu_singular(LU, k);
+    for (int i = 0; i < k; i++) {
+        if (bad) { se[i] = NAN; continue; }
+        for (int j = 0; j < k; j++) e[j] = (j == i) ? 1.0 : 0.0;
+        lu_solve(LU, perm, k, e, col);
+        se[i] = sqrt(scale * col[i]);
+    }
+}
+
 // ---- Gaussian child, method = "mle": src/irls_gaussian_fast.cpp:34-49 from Gram blocks ---------
 ABN_HDN void gauss_mle_fit(const DataMeta &m, const FitDesc &d, double *loglik, double *aic, double *bic, int *status,
-                           double *coef = nullptr)
+                           double *coef = nullptr, double *se = nullptr)
 {
     const int k = d.k;
     double A[MAXM * MAXM], S[MAXM * MAXM], b[MAXM], x[MAXM];
@@ -154,6 +173,7 @@ ABN_HDN void gauss_mle_fit(const DataMeta &m, const FitDesc &d, double *loglik, 
     *status = (st < 0 || !isfinite(ll)) ? FIT_NON_FINITE : FIT_OK;
     if (coef)
         for (int i = 0; i < k; i++) coef[i] = x[i];
+    if (se) se_from_information(A, k, ssr / (n - (double)k), se); // R/fitabn_mle.R:712-722
 }
 
 // ---- Bayes start values: beta0 = inv(X'X) X'y~ by LU, as generate_inits_n* do -------------------
@@ -283,6 +303,17 @@ ABN_HD void write_coef(const ResultPtrs &out, long long row, const FitDesc &d, c
     for (int j = 0; j < d.k; j++)
         if (off + j < out.coef_stride) o[off + j] = x[j];
     if (M > d.k && 1 + d.kdata < out.coef_stride) o[1 + d.kdata] = x[d.k];
+}
+
+// standard errors of a finished mle fit whose state holds V = X'WX of its last iteration in s.J
+ABN_HD void write_se(const ResultPtrs &out, long long row, const FitDesc &d, const FitState &s, int method)
+{
+    if (!out.se || method != MLE || s.status == FIT_NON_FINITE) return;
+    double se[MAXM];
+    se_from_information(s.J, d.k, 1.0, se);
+    ResultPtrs o = out;
+    o.coef = out.se;
+    write_coef(o, row, d, se, d.k);
 }
 
 // MDL of a scored mle row: bic + (1 + #selected stored columns - num.na) * log(nvars), _mle.R:343

@@ -31,6 +31,7 @@ struct ResultPtrs {
     int *status, *iters;
     double *coef;    // optional [rows x coef_stride]: fitted coefficients / posterior modes (plan.cuh write_coef)
     int coef_stride;
+    double *se;      // optional, same shape: mle standard errors (plan.cuh se_from_information)
 };
 
 } // namespace abnc

@@ -160,6 +160,10 @@ typedef struct abn_result {
     double *coef;
     int32_t coef_stride;
     int32_t reserved;
+    /* Optional, needs coef (same shape and slots), mle only: the standard errors fitAbn(method = "mle") reports,
+     * sqrt(diag(solve(varcov))) of the IRLS functions' `varcov` = X'WX of the last iteration for binomial and
+     * Poisson children, sqrt(diag(mse * solve(X'X))) for Gaussian ones (R/fitabn_mle.R:712-745). Bayes: NaN. */
+    double *se;
 } abn_result;
 
 typedef struct abn_data abn_data; /* opaque: device-resident data set + its global Gram     */

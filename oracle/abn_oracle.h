@@ -54,6 +54,7 @@ typedef struct or_fit {
     int status;    /* ABN_FIT_*                                                                */
     int rank;      /* mle: rank of the design as rank_cpp sees it                              */
     double coef[OR_MAXCOEF];
+    double se[OR_MAXCOEF]; /* mle: the standard errors fitAbn derives from the fit's `varcov`, R/fitabn_mle.R:715-745 */
 } or_fit;
 
 /* MLE: X column-major n x k INCLUDING the intercept column when the model has one. */

@@ -47,6 +47,21 @@ static int all_finite(const double *v, long n)
 
 int or_rank_cpp(const double *X, long n, int k) { return or_rank(X, n, k); }
 
+/* se[i] = sqrt(scale * inv(V)[i][i]), V k x k row-major (R: sqrt(diag(solve(varcov))), fitabn_mle.R:730,741;
+ * Gaussian: sqrt(diag(mse * solve(t(X) %*% X))), :722); NaN where V is singular */
+static void se_from_information(const double *V, int k, double scale, double *se)
+{
+    double LU[OR_MAXM * OR_MAXM], inv[OR_MAXM * OR_MAXM];
+    int perm[OR_MAXM], signum;
+    memcpy(LU, V, sizeof(double) * k * k);
+    or_lu_decomp(LU, k, perm, &signum);
+    if (or_lu_singular(LU, k) || or_lu_invert(LU, perm, k, inv) != 0) {
+        for (int i = 0; i < k; i++) se[i] = NAN;
+        return;
+    }
+    for (int i = 0; i < k; i++) se[i] = sqrt(scale * inv[i * k + i]);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 void or_mle_gaussian(const double *X, const double *y, long n, int k, or_fit *out)
 {
@@ -68,6 +83,7 @@ void or_mle_gaussian(const double *X, const double *y, long n, int k, or_fit *ou
     out->passes = 1;
     out->status = (st < 0 || !isfinite(out->loglik)) ? ABN_FIT_NON_FINITE : ABN_FIT_OK;
     memcpy(out->coef, x, sizeof(double) * k);
+    se_from_information(G, k, ssr / (dn - (double)k), out->se); /* mse = sse / df, df = n - (parents + 1), fitabn_mle.R:712-722 */
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -115,6 +131,7 @@ static void mle_binomial_any(const double *X, const double *y, long n, int k, in
     out->status = (failed || !isfinite(out->loglik)) ? ABN_FIT_NON_FINITE
                   : (converged ? ABN_FIT_OK : ABN_FIT_NOT_CONVERGED);
     memcpy(out->coef, x, sizeof(double) * k);
+    se_from_information(G, k, 1.0, out->se);                  /* varcov = varmatrix of the last loop pass */
     free(eta); free(W); free(z);
 }
 
@@ -211,6 +228,9 @@ void or_mle_poisson(const double *X, const double *y, long n, int k, int maxit, 
     out->status = !isfinite(out->loglik) ? ABN_FIT_NON_FINITE
                   : ((converged && !stopped_bad) ? ABN_FIT_OK : ABN_FIT_NOT_CONVERGED);
     memcpy(out->coef, x, sizeof(double) * k);
+    for (long j = 0; j < n; j++) { W[j] = exp(eta[j]); z[j] = 0.0; }  /* :142 varmatrix = A' diag(exp(eta)) A */
+    weighted_gram(X, n, k, W, z, G, rhs);
+    se_from_information(G, k, 1.0, out->se);
     free(eta); free(W); free(z); free(f); free(eta2);
 }
 

@@ -28,6 +28,7 @@ class Fit(C.Structure):
         ("status", C.c_int),
         ("rank", C.c_int),
         ("coef", C.c_double * OR_MAXCOEF),
+        ("se", C.c_double * OR_MAXCOEF),
     ]
 
 
@@ -115,7 +116,7 @@ def _xy(X, y):
 
 def _fit_dict(f: Fit, ncoef: int):
     return {"loglik": f.loglik, "aic": f.aic, "bic": f.bic, "iters": f.iters, "passes": f.passes,
-            "status": f.status, "coef": np.array(f.coef[:ncoef])}
+            "status": f.status, "coef": np.array(f.coef[:ncoef]), "se": np.array(f.se[:ncoef])}
 
 
 def mle_gaussian(X, y):

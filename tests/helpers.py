@@ -71,12 +71,12 @@ def sim_lib(wide=False):
     return _sim[key]
 
 
-def sim_score(P: prep.Prepared, children0, parents, ctrl, wide=False, coef_stride=0):
+def sim_score(P: prep.Prepared, children0, parents, ctrl, wide=False, coef_stride=0, se=False):
     """The product's solver state machines driven on the CPU (tests/host_sim.cpp); wide=True uses the
     MAXK = 32 build of the same headers (the limits of abn_b200/csrc/wide.cu)."""
     ds, k1 = capi.make_dataset(P.X, P.node_family, P.node_col0)
     cd, k2 = capi.make_candidates(children0, parents)
-    res, arrs = capi.make_result(cd.rows, ctrl.method, coef_stride)
+    res, arrs = capi.make_result(cd.rows, ctrl.method, coef_stride, se)
     buckets = np.zeros(max(1, cd.rows), dtype=np.intc)
     rc = sim_lib(wide).sim_score_cache(C.byref(ds), C.byref(cd), C.byref(ctrl), C.byref(res),
                                    buckets.ctypes.data_as(C.POINTER(C.c_int)))
@@ -90,12 +90,12 @@ def oracle_score(P: prep.Prepared, children0, parents, ctrl, threads=0):
     return pyoracle.score_cache(P.X, P.node_family, P.node_col0, children0, parents, ctrl, threads)
 
 
-def gpu_score(P: prep.Prepared, children0, parents, ctrl, device=0, coef_stride=0):
+def gpu_score(P: prep.Prepared, children0, parents, ctrl, device=0, coef_stride=0, se=False):
     """Through the C ABI: abn_b200_score_cache (one shot, host buffers in and out)."""
     L = capi.lib()
     ds, k1 = capi.make_dataset(P.X, P.node_family, P.node_col0)
     cd, k2 = capi.make_candidates(children0, parents)
-    res, arrs = capi.make_result(cd.rows, ctrl.method, coef_stride)
+    res, arrs = capi.make_result(cd.rows, ctrl.method, coef_stride, se)
     err = C.create_string_buffer(512)
     ctrl.device = device
     capi.check(L.abn_b200_score_cache(C.byref(ds), C.byref(cd), C.byref(ctrl), C.byref(res), err, len(err)), err)

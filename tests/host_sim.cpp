@@ -182,8 +182,10 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
         if (buckets) buckets[r] = bucket_of(d);
         double ll = NAN, aic = NAN, bic = NAN, mdl = NAN;
         int status = FIT_NON_FINITE, passes = 0;
-        ResultPtrs rp{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out->coef, out->coef ? out->coef_stride : 0};
+        ResultPtrs rp{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out->coef, out->coef ? out->coef_stride : 0,
+                      out->coef ? out->se : nullptr};
         if (rp.coef) for (int j = 0; j < rp.coef_stride; j++) rp.coef[r * rp.coef_stride + j] = NAN;
+        if (rp.se) for (int j = 0; j < rp.coef_stride; j++) rp.se[r * rp.coef_stride + j] = NAN;
         if (d.err || d.k == 0 || (d.family == MULTINOMIAL && (d.nlev < 2 || d.nlev > MN_MAXL || c.method != MLE || d.k > 8))) {
             // not supported by this build
         } else if (d.family == MULTINOMIAL) {
@@ -195,9 +197,10 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             while (more) { mn_pass(m, d, s.b, a); more = mn_consume(s, a); }
             ll = s.loglik; aic = s.aic; bic = s.bic; status = s.status; passes = s.passes;
         } else if (c.method == MLE && d.family == GAUSSIAN) {
-            double x[MAXM];
-            gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x);
+            double x[MAXM], se[MAXM];
+            gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x, rp.se ? se : nullptr);
             write_coef(rp, r, d, x, d.k);
+            if (rp.se) { ResultPtrs o = rp; o.coef = rp.se; write_coef(o, r, d, se, d.k); }
             passes = 1;
         } else {
             FitState s;
@@ -225,6 +228,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             ll = s.loglik; aic = s.aic; bic = s.bic; status = s.status;
             passes = d.family == GAUSSIAN ? 1 : s.passes;
             write_coef(rp, r, d, s.x, s.M);
+            write_se(rp, r, d, s, c.method);
         }
         if (c.method == MLE) mdl = mdl_of(bic, d, c.nvars);
         if (out->mlik) out->mlik[r] = ll;

@@ -221,6 +221,44 @@ def test_binomial_without_bias_reduction():
         assert abs(fast["mlik"][i] - ref["loglik"]) < 1e-10 * abs(ref["loglik"])
 
 
+def test_fit_abn_mle_on_a_dag():
+    """abn_b200.fitAbn (R/fitabn_mle.R on the same kernels): scores, coefficients and standard errors per node
+    against the oracle's single-fit entry points; binomial children without the bias reduction."""
+    import abn_b200
+    from oracle import pyoracle
+    z, names, data, dists = _ex1()
+    d = len(names)
+    rng = np.random.default_rng(21)
+    dag = np.zeros((d, d), dtype=int)
+    for i in range(d):
+        ps = rng.choice([j for j in range(i)], size=min(i, int(rng.integers(0, 4))), replace=False) if i else []
+        for p in ps:
+            if dists[names[p]] != "poisson" or dists[names[i]] != "binomial":   # keep the plain binomial fits finite
+                dag[i, p] = 1
+    fit = abn_b200.fitAbn(dag, data, dists, method="mle")
+    P = prep.prepare(data, dists, "mle")
+    X = np.asarray(P.X)
+    total = 0.0
+    for i, nm in enumerate(names):
+        ps = np.flatnonzero(dag[i])
+        D = np.column_stack([np.ones(X.shape[0])] + [X[:, P.node_col0[p]] for p in ps])
+        y = X[:, P.node_col0[i]]
+        ref = {capi.GAUSSIAN: pyoracle.mle_gaussian, capi.BINOMIAL: pyoracle.mle_binomial,
+               capi.POISSON: pyoracle.mle_poisson}[P.node_family[i]](D, y)
+        assert ref["status"] == 0 and fit["error.code"][nm] == 0
+        assert abs(fit["mliknode"][nm] - ref["loglik"]) < 1e-10 * abs(ref["loglik"])
+        assert abs(fit["aicnode"][nm] - ref["aic"]) < 1e-10 * abs(ref["aic"])
+        assert abs(fit["bicnode"][nm] - ref["bic"]) < 1e-10 * abs(ref["bic"])
+        coef = np.array(list(fit["coef"][nm].values()))
+        se = np.array(list(fit["Stderror"][nm].values()))
+        assert list(fit["coef"][nm])[0] == f"{nm}|intercept" and len(coef) == 1 + len(ps)
+        assert np.abs(coef - ref["coef"]).max() < 1e-7 * (1 + np.abs(ref["coef"]).max())
+        assert (np.abs(se - ref["se"]) < 1e-6 * ref["se"]).all()
+        assert fit["df"][nm] == X.shape[0] - (len(ps) + 1)
+        total += ref["loglik"]
+    assert abs(fit["mlik"] - total) < 1e-10 * abs(total)
+
+
 def test_edge_cases():
     names, data, dists = synth.make_columns(64, ["gaussian", "binomial", "poisson"], seed=3)
     P = prep.prepare(data, dists, "mle")

@@ -340,3 +340,32 @@ def test_binomial_mle_without_bias_reduction_is_plain_logistic_regression():
     # and it is a different estimator from the bias-reduced one the cache uses
     br = H.sim_score(P, ch, par, H.control("mle", d))
     assert np.abs(br["mlik"] - sim["mlik"]).max() > 1e-6
+
+
+def test_standard_errors_match_the_oracle():
+    """abn_result.se: sqrt(diag(solve(varcov))) as fitAbn(method = "mle") reports it (R/fitabn_mle.R:712-745)."""
+    z, names, data, dists = _case("ex1_bayes.npz")
+    d = len(names)
+    P = prep.prepare(data, dists, "mle")
+    rng = np.random.default_rng(13)
+    rows = []
+    for ch in range(d):
+        others = [j for j in range(d) if j != ch]
+        for k in (0, 2, 3):
+            rows.append((ch, sorted(rng.choice(others, k, replace=False).tolist()) + [-1] * (3 - k)))
+    ch = np.array([r[0] for r in rows], np.int32)
+    par = np.array([r[1] for r in rows], np.int32)
+    sim = H.sim_score(P, ch, par, H.control("mle", d, **{"exact.path": True}), coef_stride=5, se=True)
+    fast = H.sim_score(P, ch, par, H.control("mle", d), coef_stride=5, se=True)
+    checked = 0
+    for i in range(len(ch)):
+        ref = H.oracle_coef(P, ch[i], par[i], "mle")
+        if ref["status"] != 0 or sim["status"][i] != 0:
+            continue
+        k = len(ref["coef"])
+        assert np.isnan(sim["se"][i][k:]).all()
+        assert (np.abs(sim["se"][i][:k] - ref["se"]) < 1e-7 * ref["se"]).all(), (i, sim["se"][i], ref["se"])
+        # the shortcut path holds X'WX one Newton step before the end: standard errors only to ~1e-3 relative
+        assert (np.abs(fast["se"][i][:k] - ref["se"]) < 1e-2 * ref["se"]).all()
+        checked += 1
+    assert checked > 20
