@@ -79,6 +79,7 @@ class Result(C.Structure):
         ("coef_stride", C.c_int32),
         ("reserved", C.c_int32),
         ("se", c_double_p),
+        ("sse", c_double_p),
     ]
 
 
@@ -208,6 +209,8 @@ def make_result(rows: int, method: int, coef_stride: int = 0, se: bool = False):
         if se:
             arrs["se"] = np.full((rows, coef_stride), np.nan)
             res.se = ptr_d(arrs["se"])
+            arrs["sse"] = np.full(rows, np.nan)
+            res.sse = ptr_d(arrs["sse"])
     return res, arrs
 
 

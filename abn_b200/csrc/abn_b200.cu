@@ -284,6 +284,7 @@ gauss_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ desc
         gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x, out.se ? se : nullptr);
         write_coef(out, row, d, x, d.k);
         if (out.se) { ResultPtrs o = out; o.coef = out.se; write_coef(o, row, d, se, d.k); }
+        if (out.sse) out.sse[row] = sse_of(m, d, x);
         if (out.mlik) out.mlik[row] = ll;
         if (out.aic) out.aic[row] = aic;
         if (out.bic) out.bic[row] = bic;
@@ -578,7 +579,13 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
         CUDA_TRY(cudaMemsetAsync(dSe, 0xff, (size_t)rows * coef_stride * sizeof(double), s));
     }
     ResultPtrs rp{d->dRes, d->dRes + d->cap_rows, d->dRes + 2 * d->cap_rows, d->dRes + 3 * d->cap_rows, d->dStatus, d->dIters,
-                  dCoef, coef_stride, dSe};
+                  dCoef, coef_stride, dSe, nullptr};
+    double *dSse = nullptr;
+    if (out->sse) {
+        CUDA_TRY(dev_alloc(&dSse, (size_t)rows * sizeof(double), s));
+        CUDA_TRY(cudaMemsetAsync(dSse, 0xff, (size_t)rows * sizeof(double), s));
+        rp.sse = dSse;
+    }
 
     const int tb = 128;
     resolve_kernel<<<(unsigned)((rows + tb - 1) / tb), tb, 0, s>>>(d->m, c.method, rows, width, d->dChild, d->dParents,
@@ -694,6 +701,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     if (out->status) CUDA_TRY(cudaMemcpyAsync(out->status, rp.status, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (dCoef) CUDA_TRY(cudaMemcpyAsync(out->coef, dCoef, (size_t)rows * coef_stride * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (dSe) CUDA_TRY(cudaMemcpyAsync(out->se, dSe, (size_t)rows * coef_stride * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dSse) CUDA_TRY(cudaMemcpyAsync(out->sse, dSse, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
     std::vector<int> iters_host;
     int *iters_dst = out->iters;
     if (!iters_dst) { iters_host.resize(rows); iters_dst = iters_host.data(); }
@@ -701,6 +709,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     CUDA_TRY(cudaEventRecord(ev[4], s));
     dev_free(dCoef, s);
     dev_free(dSe, s);
+    dev_free(dSse, s);
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
     tr.mark("score: upload + plan + fits + download");

@@ -697,6 +697,7 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
             if (out.iters) out.iters[row] = st.passes;
             write_coef(out, row, d, st.x, st.M);
             write_se(out, row, d, st, c.method);
+            if (out.sse && c.method == MLE) out.sse[row] = sse_of(m, d, st.x);
         }
         __syncwarp();
     }

@@ -305,6 +305,22 @@ ABN_HD void write_coef(const ResultPtrs &out, long long row, const FitDesc &d, c
     if (M > d.k && 1 + d.kdata < out.coef_stride) o[1 + d.kdata] = x[d.k];
 }
 
+// `sse` of the reference's IRLS functions: e = b - A x on the scale of the linear predictor, whatever the family
+// (irls_binomial_fast.cpp:128-130, irls_poisson_fast.cpp, irls_gaussian_fast.cpp:38-39) = y'y - 2 x'X'y + x'X'X x,
+// Gram entries only
+ABN_HD double sse_of(const DataMeta &m, const FitDesc &d, const double *x)
+{
+    const long long gy = gram_col(d.ycol);
+    double s = m.G[gy * m.D + gy];
+    for (int i = 0; i < d.k; i++) {
+        const long long gi = gidx(d, i);
+        double t = -2.0 * m.G[gi * m.D + gy];
+        for (int j = 0; j < d.k; j++) t = fma(m.G[gi * m.D + gidx(d, j)], x[j], t);
+        s = fma(t, x[i], s);
+    }
+    return s;
+}
+
 // standard errors of a finished mle fit whose state holds V = X'WX of its last iteration in s.J
 ABN_HD void write_se(const ResultPtrs &out, long long row, const FitDesc &d, const FitState &s, int method)
 {

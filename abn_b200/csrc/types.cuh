@@ -32,6 +32,7 @@ struct ResultPtrs {
     double *coef;    // optional [rows x coef_stride]: fitted coefficients / posterior modes (plan.cuh write_coef)
     int coef_stride;
     double *se;      // optional, same shape: mle standard errors (plan.cuh se_from_information)
+    double *sse;     // optional [rows]: ||y - X beta||^2 as the reference's IRLS functions report it (plan.cuh sse_of)
 };
 
 } // namespace abnc

@@ -177,6 +177,7 @@ fit_wide_kernel(const DataMeta m, const Control c, const int *__restrict__ child
                     gauss_mle_fit(m, d, &ll, &aic, &bic, &status, S.st.x, out.se ? S.st.dir : nullptr);
                     write_coef(out, row, d, S.st.x, d.k);
                     if (out.se) { ResultPtrs o = out; o.coef = out.se; write_coef(o, row, d, S.st.dir, d.k); }
+                    if (out.sse) out.sse[row] = sse_of(m, d, S.st.x);
                     if (out.mlik) out.mlik[row] = ll;
                     if (out.aic) out.aic[row] = aic;
                     if (out.bic) out.bic[row] = bic;
@@ -221,6 +222,7 @@ fit_wide_kernel(const DataMeta m, const Control c, const int *__restrict__ child
             if (out.iters) out.iters[row] = S.st.passes;
             write_coef(out, row, d, S.st.x, S.st.M);
             write_se(out, row, d, S.st, c.method);
+            if (out.sse && c.method == MLE) out.sse[row] = sse_of(m, d, S.st.x);
         }
         __syncwarp();
     }

@@ -4,8 +4,8 @@ The reference's ``fitAbn.mle`` (R/fitabn_mle.R:12-230) regresses every node on i
 IRLS functions the score cache uses (``regressionLoop`` :240-840) and returns, per node, the log-likelihood,
 AIC / BIC / MDL, the coefficients and their standard errors. This mirror covers the part of it that runs on
 the B200 kernels: Gaussian, binomial and Poisson children without grouping. Not built: multinomial children
-(``nnet::multinom`` with its own standard errors), ``group.var`` (mixed models), ``sse`` / ``mse``, and
-``method = "bayes"`` (marginal densities).
+(``nnet::multinom`` with its own standard errors), ``group.var`` (mixed models) and ``method = "bayes"``
+(marginal densities).
 
 Differences to the cache path, all as in the reference: binomial children are fitted WITHOUT the bias reduction
 first (``irls_binomial_cpp_fast``, :585) and fall back to the bias-reduced fit when that fails (:586-594), and
@@ -24,7 +24,7 @@ from . import prep as _prep
 def fitAbn(dag, data_df, data_dists, method="mle", control=None, centre=True, device=0):
     """``fitAbn(dag, data.df, data.dists, method = "mle")``. ``dag`` is a d x d 0/1 matrix, row i = parents of node i
     (the reference's orientation, R/fitabn.R), or a dict ``{child: [parents]}``. Returns a dict with the
-    reference's fields: ``mliknode, mlik, aicnode, aic, bicnode, bic, mdlnode, mdl, df, coef, Stderror, method``
+    reference's fields: ``mliknode, mlik, aicnode, aic, bicnode, bic, mdlnode, mdl, df, sse, mse, coef, Stderror, method``
     plus ``error.code`` (0 ok / 1 not converged / 2 non-finite, per node)."""
     if method != "mle":
         raise NotImplementedError("only method = 'mle' is built on the B200 path (SURVEY 8f)")
@@ -62,16 +62,17 @@ def fitAbn(dag, data_df, data_dists, method="mle", control=None, centre=True, de
         redo = np.flatnonzero((P.node_family == capi.BINOMIAL) & ((plain["status"] != 0) | ~np.isfinite(plain["mlik"])))
         if len(redo):
             br = dd.score(children[redo], parents[redo], _cache.to_c_control(ctrl, "mle", d), coef_stride=stride, se=True)
-            for k in ("mlik", "aic", "bic", "mdl", "status", "coef", "se"):
+            for k in ("mlik", "aic", "bic", "mdl", "status", "coef", "se", "sse"):
                 plain[k][redo] = br[k]
 
-    out = {"mliknode": {}, "aicnode": {}, "bicnode": {}, "mdlnode": {}, "df": {}, "coef": {}, "Stderror": {},
-           "error.code": {}}
+    out = {"mliknode": {}, "aicnode": {}, "bicnode": {}, "mdlnode": {}, "df": {}, "sse": {}, "mse": {}, "coef": {},
+           "Stderror": {}, "error.code": {}}
     for i, nm in enumerate(names):
         if nm in multi_children:
             for k in ("mliknode", "aicnode", "bicnode", "mdlnode"):
                 out[k][nm] = plain[{"mliknode": "mlik", "aicnode": "aic", "bicnode": "bic", "mdlnode": "mdl"}[k]][i]
             out["df"][nm], out["coef"][nm], out["Stderror"][nm] = np.nan, None, None
+            out["sse"][nm] = out["mse"][nm] = np.nan
             out["error.code"][nm] = int(plain["status"][i])
             continue
         ps = np.flatnonzero(dag[i])
@@ -88,6 +89,8 @@ def fitAbn(dag, data_df, data_dists, method="mle", control=None, centre=True, de
         out["bicnode"][nm] = float(plain["bic"][i])
         out["mdlnode"][nm] = float(plain["mdl"][i])
         out["df"][nm] = P.n - (len(pcols) + 1)                         # :711
+        out["sse"][nm] = float(plain["sse"][i])                        # :712
+        out["mse"][nm] = out["sse"][nm] / out["df"][nm]                # :713
         out["coef"][nm] = dict(zip(labels, plain["coef"][i][sl]))
         out["Stderror"][nm] = dict(zip(labels, plain["se"][i][sl]))
         out["error.code"][nm] = int(plain["status"][i])

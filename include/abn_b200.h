@@ -164,6 +164,9 @@ typedef struct abn_result {
      * sqrt(diag(solve(varcov))) of the IRLS functions' `varcov` = X'WX of the last iteration for binomial and
      * Poisson children, sqrt(diag(mse * solve(X'X))) for Gaussian ones (R/fitabn_mle.R:712-745). Bayes: NaN. */
     double *se;
+    /* Optional [rows], mle only: the `sse` of the reference's IRLS functions, ||y - X beta||^2 on the scale of the
+     * linear predictor whatever the family (src/irls_binomial_fast.cpp:128-130); fitAbn's mse = sse / df. */
+    double *sse;
 } abn_result;
 
 typedef struct abn_data abn_data; /* opaque: device-resident data set + its global Gram     */

@@ -183,7 +183,8 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
         double ll = NAN, aic = NAN, bic = NAN, mdl = NAN;
         int status = FIT_NON_FINITE, passes = 0;
         ResultPtrs rp{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out->coef, out->coef ? out->coef_stride : 0,
-                      out->coef ? out->se : nullptr};
+                      out->coef ? out->se : nullptr, out->sse};
+        if (rp.sse) rp.sse[r] = NAN;
         if (rp.coef) for (int j = 0; j < rp.coef_stride; j++) rp.coef[r * rp.coef_stride + j] = NAN;
         if (rp.se) for (int j = 0; j < rp.coef_stride; j++) rp.se[r * rp.coef_stride + j] = NAN;
         if (d.err || d.k == 0 || (d.family == MULTINOMIAL && (d.nlev < 2 || d.nlev > MN_MAXL || c.method != MLE || d.k > 8))) {
@@ -201,6 +202,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x, rp.se ? se : nullptr);
             write_coef(rp, r, d, x, d.k);
             if (rp.se) { ResultPtrs o = rp; o.coef = rp.se; write_coef(o, r, d, se, d.k); }
+            if (rp.sse) rp.sse[r] = sse_of(m, d, x);
             passes = 1;
         } else {
             FitState s;
@@ -229,6 +231,7 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             passes = d.family == GAUSSIAN ? 1 : s.passes;
             write_coef(rp, r, d, s.x, s.M);
             write_se(rp, r, d, s, c.method);
+            if (rp.sse && c.method == MLE) rp.sse[r] = sse_of(m, d, s.x);
         }
         if (c.method == MLE) mdl = mdl_of(bic, d, c.nvars);
         if (out->mlik) out->mlik[r] = ll;

@@ -62,6 +62,8 @@ def test_fit_abn_mle_matches_the_oracle_node_by_node(monkeypatch):
         assert np.abs(coef - ref["coef"]).max() < 1e-7 * (1 + np.abs(ref["coef"]).max())
         assert (np.abs(se - ref["se"]) < 1e-6 * ref["se"]).all()
         assert fit["df"][nm] == X.shape[0] - (len(ps) + 1)
+        sse = float(((X[:, P.node_col0[i]] - D @ ref["coef"]) ** 2).sum())   # e = b - A x, irls_*_fast.cpp
+        assert abs(fit["sse"][nm] - sse) < 1e-8 * sse and abs(fit["mse"][nm] - sse / fit["df"][nm]) < 1e-8 * sse
         total += ref["loglik"]
     assert abs(fit["mlik"] - total) < 1e-10 * abs(total) and fit["method"] == "mle"
     # the dict form of the DAG gives the same fit

@@ -255,6 +255,8 @@ def test_fit_abn_mle_on_a_dag():
         assert np.abs(coef - ref["coef"]).max() < 1e-7 * (1 + np.abs(ref["coef"]).max())
         assert (np.abs(se - ref["se"]) < 1e-6 * ref["se"]).all()
         assert fit["df"][nm] == X.shape[0] - (len(ps) + 1)
+        sse = float(((y - D @ ref["coef"]) ** 2).sum())
+        assert abs(fit["sse"][nm] - sse) < 1e-8 * sse
         total += ref["loglik"]
     assert abs(fit["mlik"] - total) < 1e-10 * abs(total)
 
