@@ -4,8 +4,8 @@ The reference's ``fitAbn.mle`` (R/fitabn_mle.R:12-230) regresses every node on i
 IRLS functions the score cache uses (``regressionLoop`` :240-840) and returns, per node, the log-likelihood,
 AIC / BIC / MDL, the coefficients and their standard errors. This mirror covers the part of it that runs on
 the B200 kernels: Gaussian, binomial and Poisson children without grouping. Not built: multinomial children
-(``nnet::multinom`` with its own standard errors), ``group.var`` (mixed models) and ``method = "bayes"``
-(marginal densities).
+(``nnet::multinom`` with its own standard errors) and ``group.var`` (mixed models). ``method = "bayes"`` returns
+the modes and log marginal likelihoods only (``compute.fixed = FALSE``), no marginal densities.
 
 Differences to the cache path, all as in the reference: binomial children are fitted WITHOUT the bias reduction
 first (``irls_binomial_cpp_fast``, :585) and fall back to the bias-reduced fit when that fails (:586-594), and
@@ -26,8 +26,8 @@ def fitAbn(dag, data_df, data_dists, method="mle", control=None, centre=True, de
     (the reference's orientation, R/fitabn.R), or a dict ``{child: [parents]}``. Returns a dict with the
     reference's fields: ``mliknode, mlik, aicnode, aic, bicnode, bic, mdlnode, mdl, df, sse, mse, coef, Stderror, method``
     plus ``error.code`` (0 ok / 1 not converged / 2 non-finite, per node)."""
-    if method != "mle":
-        raise NotImplementedError("only method = 'mle' is built on the B200 path (SURVEY 8f)")
+    if method not in ("mle", "bayes"):
+        raise ValueError("`method` unknown.")
     cols = _prep.as_columns(data_df)
     names = [c.name for c in cols]
     if set(data_dists) != set(names):
@@ -42,6 +42,8 @@ def fitAbn(dag, data_df, data_dists, method="mle", control=None, centre=True, de
     dag = np.asarray(dag)
     if dag.shape != (d, d) or (np.diag(dag) != 0).any():
         raise ValueError("`dag` must be a d x d 0/1 matrix with an empty diagonal")
+    if method == "bayes":
+        return _fit_bayes(dag, names, data_df, data_dists, control, centre, device)
     P = _prep.prepare(data_df, data_dists, "mle", centre=centre)
     multi_children = [names[i] for i in range(d) if P.node_family[i] == capi.MULTINOMIAL]
     width = max(1, int(dag.sum(axis=1).max()))
@@ -99,5 +101,47 @@ def fitAbn(dag, data_df, data_dists, method="mle", control=None, centre=True, de
     out["bic"] = float(np.nansum(list(out["bicnode"].values())))
     out["mdl"] = float(np.nansum(list(out["mdlnode"].values())))
     out["method"] = "mle"
+    out["dag"] = dag
+    return out
+
+
+_ERROR_DESC = {0: "success", 1: "warning: mode results may be unreliable (optimiser terminated unusually)",
+               2: "error - logscore is NA - model could not be fitted"}  # R/fitabn_bayes.R:172-176
+
+
+def _fit_bayes(dag, names, data_df, data_dists, control, centre, device):
+    """``fitAbn(method = "bayes", compute.fixed = FALSE)`` (R/fitabn_bayes.R:60-180, 536-565): per node the Laplace
+    log marginal likelihood and the posterior modes ``fit_single_node`` leaves behind (src/fit_single_node.c:182-194),
+    named ``child|(Intercept)``, ``child|parent`` and, for a Gaussian node, ``child|precision``. Marginal densities
+    (``compute.fixed = TRUE``) and ``mse`` are not built."""
+    d = len(names)
+    P = _prep.prepare(data_df, data_dists, "bayes", centre=centre)
+    width = max(1, int(dag.sum(axis=1).max()))
+    children = np.arange(d, dtype=np.int32)
+    parents = np.full((d, width), -1, dtype=np.int32)
+    for i in range(d):
+        ps = np.flatnonzero(dag[i])
+        parents[i, :len(ps)] = ps
+    ctrl = dict(_cache._check_control(control, "bayes"))
+    ctrl["device"] = device
+    with _cache.DeviceData(P, device) as dd:
+        res = dd.score(children, parents, _cache.to_c_control(ctrl, "bayes", d), coef_stride=width + 2)
+    out = {"modes": {}, "error.code": {}, "error.code.desc": {}, "hessian.accuracy": {}, "mliknode": {}, "used.INLA": {}}
+    for i, nm in enumerate(names):
+        ps = np.flatnonzero(dag[i])
+        labels = [f"{nm}|(Intercept)"] + [f"{nm}|{names[p]}" for p in ps]
+        vals = list(res["coef"][i][:1 + len(ps)])
+        if P.node_family[i] == capi.GAUSSIAN:
+            labels.append(f"{nm}|precision")
+            vals.append(res["coef"][i][1 + len(ps)])
+        out["modes"][nm] = dict(zip(labels, (float(v) for v in vals)))
+        out["error.code"][nm] = int(res["status"][i])
+        out["error.code.desc"][nm] = _ERROR_DESC.get(int(res["status"][i]), str(int(res["status"][i])))
+        out["hessian.accuracy"][nm] = 0.0
+        out["mliknode"][nm] = float(res["mlik"][i])
+        out["used.INLA"][nm] = False
+    out["mlik"] = float(sum(out["mliknode"].values()))
+    out["coef"] = {nm: list(m.values()) for nm, m in out["modes"].items()}   # modes2coefs
+    out["method"] = "bayes"
     out["dag"] = dag
     return out

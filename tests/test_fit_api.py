@@ -92,10 +92,37 @@ def test_fit_abn_binomial_falls_back_to_the_bias_reduced_fit(monkeypatch):
         assert abs(fit["mliknode"]["b"] - ref["loglik"]) < 1e-8 * abs(ref["loglik"])
 
 
+def test_fit_abn_bayes_modes_and_mlik(monkeypatch):
+    """fitAbn(method = "bayes", compute.fixed = FALSE): modes and Laplace mlik per node vs the oracle's GSL-hybrid path."""
+    monkeypatch.setattr(abncache, "DeviceData", _SimData)
+    names, data, dists = _ex1()
+    d = len(names)
+    rng = np.random.default_rng(4)
+    dag = np.zeros((d, d), dtype=int)
+    for i in range(1, d):
+        for p in rng.choice(np.arange(i), size=min(i, int(rng.integers(0, 3))), replace=False):
+            dag[i, p] = 1
+    fit = abn_b200.fitAbn(dag, data, dists, method="bayes")
+    P = prep.prepare(data, dists, "bayes")
+    X = np.asarray(P.X)
+    for i, nm in enumerate(names):
+        ps = np.flatnonzero(dag[i])
+        D = np.column_stack([np.ones(X.shape[0])] + [X[:, P.node_col0[p]] for p in ps])
+        ref = pyoracle.bayes_fit(P.node_family[i], D, X[:, P.node_col0[i]], solver=capi.SOLVER_HYBRID)
+        assert fit["error.code"][nm] == ref["status"] == 0 and fit["error.code.desc"][nm] == "success"
+        assert abs(fit["mliknode"][nm] - ref["loglik"]) < 1e-9 * abs(ref["loglik"])
+        modes = fit["modes"][nm]
+        want = [f"{nm}|(Intercept)"] + [f"{nm}|{names[p]}" for p in ps] + ([f"{nm}|precision"] if dists[nm] == "gaussian" else [])
+        assert list(modes) == want
+        got = np.array(list(modes.values()))
+        assert np.abs(got - ref["coef"]).max() < 1e-7 * (1 + np.abs(ref["coef"]).max())
+    assert abs(fit["mlik"] - sum(fit["mliknode"].values())) < 1e-9 and fit["method"] == "bayes"
+
+
 def test_fit_abn_argument_checks():
     names, data, dists = _ex1()
-    with pytest.raises(NotImplementedError):
-        abn_b200.fitAbn(np.zeros((10, 10), int), data, dists, method="bayes")
+    with pytest.raises(ValueError):
+        abn_b200.fitAbn(np.zeros((10, 10), int), data, dists, method="inla")
     with pytest.raises(ValueError):
         abn_b200.fitAbn(np.eye(10, dtype=int), data, dists)
     with pytest.raises(ValueError):

@@ -261,6 +261,31 @@ def test_fit_abn_mle_on_a_dag():
     assert abs(fit["mlik"] - total) < 1e-10 * abs(total)
 
 
+def test_fit_abn_bayes_on_a_dag():
+    """abn_b200.fitAbn(method = "bayes"): Laplace mlik and posterior modes per node vs the oracle's GSL-hybrid path."""
+    import abn_b200
+    from oracle import pyoracle
+    z, names, data, dists = _ex1()
+    d = len(names)
+    rng = np.random.default_rng(4)
+    dag = np.zeros((d, d), dtype=int)
+    for i in range(1, d):
+        for p in rng.choice(np.arange(i), size=min(i, int(rng.integers(0, 3))), replace=False):
+            dag[i, p] = 1
+    fit = abn_b200.fitAbn(dag, data, dists, method="bayes")
+    P = prep.prepare(data, dists, "bayes")
+    X = np.asarray(P.X)
+    for i, nm in enumerate(names):
+        ps = np.flatnonzero(dag[i])
+        D = np.column_stack([np.ones(X.shape[0])] + [X[:, P.node_col0[p]] for p in ps])
+        ref = pyoracle.bayes_fit(P.node_family[i], D, X[:, P.node_col0[i]], solver=capi.SOLVER_HYBRID)
+        assert fit["error.code"][nm] == ref["status"] == 0
+        assert abs(fit["mliknode"][nm] - ref["loglik"]) < 1e-9 * abs(ref["loglik"])
+        got = np.array(list(fit["modes"][nm].values()))
+        assert len(got) == len(ref["coef"])
+        assert np.abs(got - ref["coef"]).max() < 1e-7 * (1 + np.abs(ref["coef"]).max())
+
+
 def test_edge_cases():
     names, data, dists = synth.make_columns(64, ["gaussian", "binomial", "poisson"], seed=3)
     P = prep.prepare(data, dists, "mle")
