@@ -7,7 +7,14 @@
 // shuffles reduces them (deterministic: the same bits whatever the partition of candidates over
 // GPUs), lane 0 runs the solver state machine (solver.cuh) on the warp's shared-memory state and
 // broadcasts the next evaluation point. Tensor cores are not used: the work per row is a few
-// dozen FP64 flops against 8(k+1) streamed bytes.
+// dozen FP64 flops against 8 k_data streamed bytes.
+//
+// Designs with an intercept (all of them unless the rank rule drops it) never stream the response:
+// X'y and X'1 come from the global Gram matrix, so the Poisson pass (warp_pass_pois) needs only
+// H = sum E x x' - its first row gives the score, H_00 the log-likelihood - and the binomial pass
+// (warp_pass_bin) one extra vector sum. The generic passes (warp_pass, warp_pass_staged) remain
+// for designs without an intercept and for the reference's Poisson start-value pass
+// (ABN_FLAG_EXACT_PATH).
 //
 // Work is handed out by a global atomic counter over a candidate list that keeps the cache
 // order (same child, shared leading parents adjacent), so warps that run concurrently read the
