@@ -127,3 +127,28 @@ def test_fit_abn_argument_checks():
         abn_b200.fitAbn(np.eye(10, dtype=int), data, dists)
     with pytest.raises(ValueError):
         abn_b200.fitAbn(np.zeros((3, 3), int), data, dists)
+
+
+def test_fit_abn_with_a_multinomial_parent_has_no_intercept(monkeypatch):
+    """R/fitabn_mle.R:546-548: a multinomial parent is expanded into its level columns and the design has no
+    intercept; the coefficient names are the level columns (:806-808)."""
+    monkeypatch.setattr(abncache, "DeviceData", _SimData)
+    rng = np.random.default_rng(8)
+    n = 600
+    codes = rng.integers(1, 4, size=n)
+    g = rng.normal(size=n)
+    y = (rng.random(n) < 1 / (1 + np.exp(-(0.4 * g + 0.5 * (codes == 2) - 0.3)))).astype(float)
+    data = {"b": y, "g": g, "m": (codes, ["x", "y", "z"])}
+    dists = {"b": "binomial", "g": "gaussian", "m": "multinomial"}
+    fit = abn_b200.fitAbn({"b": ["g", "m"], "g": [], "m": []}, data, dists)
+    P = prep.prepare(data, dists, "mle")
+    X = np.asarray(P.X)
+    cols = [P.node_col0[1]] + list(range(P.node_col0[2], P.node_col0[3]))
+    D = np.column_stack([X[:, c] for c in cols])                       # no intercept
+    ref = pyoracle.mle_binomial(D, X[:, P.node_col0[0]])
+    assert ref["status"] == 0 and fit["error.code"]["b"] == 0
+    assert list(fit["coef"]["b"]) == [P.col_names[c] for c in cols]
+    assert abs(fit["mliknode"]["b"] - ref["loglik"]) < 1e-10 * abs(ref["loglik"])
+    assert np.abs(np.array(list(fit["coef"]["b"].values())) - ref["coef"]).max() < 1e-7
+    assert (np.abs(np.array(list(fit["Stderror"]["b"].values())) - ref["se"]) < 1e-6 * ref["se"]).all()
+    assert fit["coef"]["m"] is None and np.isfinite(fit["mliknode"]["m"])   # multinomial child: scores only
