@@ -54,6 +54,8 @@ def main():
         mlik = np.asarray(cache["mlik"], dtype=float)
         ok = (ref["status"] == 0) & np.isfinite(ref["mlik"])
         code = np.asarray(cache["error.code"]) if "error.code" in cache else None
+        if code is not None and code.shape != ref["status"].shape:
+            code = None                                   # mle caches carry no error.code
         out[method] = {"fits": int(rows), "seconds": dt, "fits_per_s": rows / dt,
                        "oracle_seconds_all_cores": dt_ref,
                        "max_rel_diff_vs_oracle_ok_rows": float(H.rel_err(mlik[ok], ref["mlik"][ok]).max()),
