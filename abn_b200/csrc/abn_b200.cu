@@ -655,13 +655,13 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
                 else mfn = get_launch_mn(fam, k, icpt);
                 if (mfn) {
                     int grid = std::min((count + MN_WARPS - 1) / MN_WARPS, d->sm_count * 2);
-                    mfn(d->m, c, d->dDescs, list, count, d->dCounters + b, rp, grid, ks);
+                    CUDA_TRY(mfn(d->m, c, d->dDescs, list, count, d->dCounters + b, rp, grid, ks));
                 } else if (!fn) {
                     n_unsupported += count;
                     unsupported_kernel<<<(count + 255) / 256, 256, 0, ks>>>(list, count, rp);
                 } else {
                     int grid = std::min((count + FIT_WARPS - 1) / FIT_WARPS, d->sm_count * ABN_MIN_BLOCKS);
-                    fn(d->m, c, d->dDescs, d->dChild, list, count, d->dCounters + b, rp, grid, ks);
+                    CUDA_TRY(fn(d->m, c, d->dDescs, d->dChild, list, count, d->dCounters + b, rp, grid, ks));
                 }
             }
             {

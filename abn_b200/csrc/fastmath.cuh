@@ -119,6 +119,50 @@ ABN_HD double fast_exp(double t, const double *tab)
     return with_hi_word(v, hi_word(v) + (int)(((uint32_t)n << 14) & 0xfff00000u));
 }
 
+// ---- exp for the lean passes: 256-entry table with pre-scaled exponent words ----------------------
+// Same scheme as fast_exp with n = 256 k + j, |r| <= ln2/512, so the polynomial stops at r^4 (the r^5
+// term is < 4e-17) - 9 FP64 instructions - and with the integer side cut to three instructions:
+// the shared-memory copy of the table stores 2^(j/256) with (j << 12) taken off its high word, so
+//     hi(2^k 2^(j/256)) = hi(entry_j) + (n << 12)        (one shift-add; n << 12 = (k << 20) + (j << 12))
+// and the scaling is applied to the table entry BEFORE the last fma, which then yields exp(t) itself.
+// Valid for |t| <= 700 (callers check the range after the pass; nothing clamps here).
+#define ABN_EXP256_N 256
+#if defined(__CUDACC__)
+__constant__ double c_exp2_256_table[ABN_EXP256_N] = {
+#include "exp2_256_table.inc"
+};
+#endif
+static const double h_exp2_256_table[ABN_EXP256_N] = {
+#include "exp2_256_table.inc"
+};
+
+// entry j of the pre-scaled table from the plain one
+ABN_HD double exp256_entry(double two_j_256, int j)
+{
+    return with_hi_word(two_j_256, hi_word(two_j_256) - (j << 12));
+}
+
+ABN_HD double fast_exp256(double t, const double *tab)
+{
+    const double MAGIC = 6755399441055744.0;         // 1.5 * 2^52
+    const double INV = 369.329833984375;             // 256 / ln 2 to 21 bits (0x40771547 00000000)
+    const double LN2_256_HI = 0.002707604318857193;  // 0x3f662e42 00000000
+    const double LN2_256_LO = 1.855205093371747e-09; // ln2/256 - HI
+    const double C4 = 0.041666656732559204;          // 1/24 (0x3fa55555 00000000)
+    const double kd = fma(t, INV, MAGIC);
+    const double nf = kd - MAGIC;
+    double r = fma(nf, -LN2_256_HI, t);              // exact
+    r = fma(nf, -LN2_256_LO, r);
+    const int n = (int)(uint32_t)double_to_bits(kd);
+    // p(r) = r + r^2/2 + r^3/6 + r^4/24, |r| <= 0.00136
+    double p = fma(r, C4, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p * r, r, r);
+    const double tj = tab[n & 255];
+    const double ts = with_hi_word(tj, hi_word(tj) + (int)((uint32_t)n << 12)); // 2^k 2^(j/256)
+    return fma(ts, p, ts);
+}
+
 // 1 / d, correctly rounded for normal d with a normal result. MUFU.RCP64H seeds ~2^-20; one step
 // with cubic convergence (x (1 + e + e^2)) lands within an ulp; then Markstein's correction
 // r = fma(-d, x, 1), x + x r rounds correctly unless d's mantissa is all ones.

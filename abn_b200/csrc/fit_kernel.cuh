@@ -187,11 +187,23 @@ __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const do
 #endif
 constexpr int FIT_STAGES = 2;
 
-// bytes of dynamic shared memory the staged pass needs per CTA
+#ifndef ABN_LEAN_STAGES
+#define ABN_LEAN_STAGES 3
+#endif
+// doubles of tile storage one warp needs: the staged pass (FIT_STAGES x (KD + 1) columns x 32 FIT_UNROLL rows)
+// or the lean pass (ABN_LEAN_STAGES x KD columns x 128 rows), whichever is larger
+template <int K, bool ICPT>
+constexpr size_t fit_stage_doubles_per_warp()
+{
+    const size_t staged = ABN_STAGE ? (size_t)FIT_STAGES * (K - (ICPT ? 1 : 0) + 1) * 32 * FIT_UNROLL : 0;
+    const size_t lean = ICPT ? (size_t)ABN_LEAN_STAGES * (K - 1) * 128 : 0;
+    return staged > lean ? staged : lean;
+}
+// bytes of dynamic shared memory the passes need per CTA
 template <int K, bool ICPT>
 constexpr size_t fit_stage_bytes()
 {
-    return ABN_STAGE ? (size_t)FIT_WARPS * FIT_STAGES * (K - (ICPT ? 1 : 0) + 1) * 32 * FIT_UNROLL * sizeof(double) : 0;
+    return (size_t)FIT_WARPS * fit_stage_doubles_per_warp<K, ICPT>() * sizeof(double);
 }
 
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
@@ -590,11 +602,277 @@ __device__ __forceinline__ void warp_pass_bin(const double *__restrict__ y, cons
     }
 }
 
+// ---- lean passes ---------------------------------------------------------------------------------
+// The passes above are bound by instruction issue as much as by the FP64 pipe: per row they spend about as
+// many integer / load-store / branch instructions as FP64 ones (profiles/sass_r1_*), and a warp-wide FP64
+// instruction already occupies the pipe for two issue cycles. The lean passes do the same sums with the
+// non-FP64 work cut to less than half, so that the FP64 pipe alone sets the pace:
+//   * 16-byte cp.async and 16-byte shared reads: lane l owns rows 64 c + 2 l + {0, 1} of each 128-row tile
+//     (half the copy / load instructions), one 32-bit row offset instead of a pointer per column;
+//   * fast_exp256: 9 FP64 + 4 integer / LDS instructions instead of 10 + 7;
+//   * no clamps, no per-row branches, no votes: the extreme high words of eta are tracked with 3-input
+//     integer max (one VIMNMX3 per two rows and bound) and checked once after the pass. A pass that met an
+//     eta outside the range the fast row ops are exact for - eta >= 12 for the bias-reduced binomial fit
+//     (the rows where the reference's rho noise is visible, see warp_pass_bin), |eta| >= 700 or NaN
+//     elsewhere - returns false, and the careful pass above redoes it (and all later passes of that fit).
+//     On BASELINE-like data no fit ever does.
+//   * binomial, both methods: sigma = g = 1/(1+e), e = exp(-eta); w = g - g^2; sum log(1+E) = sum log(1+e)
+//     + beta'(X'1), so the Bayes passes share the mle row op and the only per-row difference is gone.
+// Rows are summed in a fixed order that depends on nothing but n, so results stay bit-identical under any
+// partition of the candidate list.
+#ifndef ABN_LEAN
+#define ABN_LEAN 1
+#endif
+#ifndef ABN_LEAN_STAGES
+#define ABN_LEAN_STAGES 3
+#endif
+constexpr int LEAN_STAGES = ABN_LEAN_STAGES;
+constexpr int LEAN_TROWS = 128;
+
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+
+// Streams the KD design columns of one fit through the warp's tiles and calls row(x) for every observation,
+// x[j] = design column j + 1; row returns the high word of its eta, whose extremes end up in tk.
+template <int KD, typename RowFn>
+__device__ __forceinline__ void lean_stream(const double *const (&cp)[MAXK], long long n, double *tile, RowTrack &tk,
+                                            RowFn &&row)
+{
+    constexpr int TR = LEAN_TROWS, ST = LEAN_STAGES;
+    constexpr int KDA = KD > 0 ? KD : 1;
+    const int lane = threadIdx.x & 31;
+    const int ntiles = (KD > 0) ? (int)(n / TR) : 0;
+    const double *base[KDA];
+#pragma unroll
+    for (int j = 0; j < KD; j++) base[j] = cp[j] + 2 * lane;
+    double *const tl = tile + 2 * lane;
+    unsigned off = 0; // first row of the next tile to issue
+    auto issue = [&](int stage) {
+        double *t = tl + stage * (KD * TR);
+#pragma unroll
+        for (int j = 0; j < KD; j++) {
+            const double *p = base[j] + off;
+            cp_async16(t + j * TR, p);
+            cp_async16(t + j * TR + 64, p + 64);
+        }
+        off += TR;
+    };
+    // one commit group per tile slot, empty once the tiles run out, so that wait_group<ST - 1> always
+    // means "the tile of this iteration has landed"
+#pragma unroll
+    for (int s = 0; s < ST - 1; s++) {
+        if (s < ntiles) issue(s);
+        cp_async_commit();
+    }
+    int stage = 0, fill = ST - 1;
+    for (int it = 0; it < ntiles; it++) {
+        if (it + ST - 1 < ntiles) issue(fill);
+        cp_async_commit();
+        cp_async_wait<ST - 1>();
+        const double *t = tl + stage * (KD * TR);
+        double x[4][KDA];
+#pragma unroll
+        for (int j = 0; j < KD; j++) {
+            const double2 a = *reinterpret_cast<const double2 *>(t + j * TR);
+            const double2 b = *reinterpret_cast<const double2 *>(t + j * TR + 64);
+            x[0][j] = a.x; x[1][j] = a.y; x[2][j] = b.x; x[3][j] = b.y;
+        }
+        const int h0 = row(x[0]), h1 = row(x[1]), h2 = row(x[2]), h3 = row(x[3]);
+        tk.smax = max(max(tk.smax, h0), h1);
+        tk.umax = max(max(tk.umax, (unsigned)h0), (unsigned)h1);
+        tk.smax = max(max(tk.smax, h2), h3);
+        tk.umax = max(max(tk.umax, (unsigned)h2), (unsigned)h3);
+        fill = stage;
+        stage = (stage + 1 == ST) ? 0 : stage + 1;
+    }
+    cp_async_wait<0>();
+    for (long long i = (long long)ntiles * TR + lane; i < n; i += 32) { // fewer than 128 rows (all of them for KD = 0)
+        double xt[KDA];
+#pragma unroll
+        for (int j = 0; j < KD; j++) xt[j] = __ldg(cp[j] + i);
+        const int h = row(xt);
+        tk.smax = max(tk.smax, h);
+        tk.umax = max(tk.umax, (unsigned)h);
+    }
+}
+
+// Poisson with an intercept (see warp_pass_pois for the identities). false: eta left (-700, 700), nothing written.
+template <int K, int MODE>
+__device__ __forceinline__ bool lean_pass_pois(const double *const (&cp)[MAXK], const double *beta_sm, const double *xty,
+                                               long long n, const double *tab256, PassAcc *acc_sm, double *tile)
+{
+    constexpr int KD = K - 1;
+    constexpr int KDA = KD > 0 ? KD : 1;
+    constexpr bool ALL_H = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_HESS);
+    constexpr int NH = ALL_H ? K * (K + 1) / 2 : (MODE == PASS_GRAD ? K : 1);
+    const int lane = threadIdx.x & 31;
+    double beta[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) beta[j] = beta_sm[j];
+    double H[NH];
+#pragma unroll
+    for (int j = 0; j < NH; j++) H[j] = 0.0;
+    RowTrack tk = row_track_init();
+    auto row = [&](const double (&x)[KDA]) -> int {
+        double eta = beta[0];
+#pragma unroll
+        for (int j = 0; j < KD; j++) eta = fma(x[j], beta[j + 1], eta);
+        const double E = fast_exp256(eta, tab256);
+        H[0] += E;
+        if (ALL_H) {
+            int t = 1;
+#pragma unroll
+            for (int q = 0; q < KD; q++) { H[t] = fma(E, x[q], H[t]); t++; }
+#pragma unroll
+            for (int p = 0; p < KD; p++) {
+                const double wx = E * x[p];
+#pragma unroll
+                for (int q = p; q < KD; q++) { H[t] = fma(wx, x[q], H[t]); t++; }
+            }
+        } else if (MODE == PASS_GRAD) {
+#pragma unroll
+            for (int q = 0; q < KD; q++) H[q + 1] = fma(E, x[q], H[q + 1]);
+        }
+        return hi_word(eta);
+    };
+    lean_stream<KD>(cp, n, tile, tk, row);
+    if (__any_sync(0xffffffffu, (tk.smax >= 0x4085E000) | (tk.umax >= 0xC085E000u))) return false; // |eta| >= 700, NaN
+#pragma unroll
+    for (int j = 0; j < NH; j++) H[j] = warp_sum(H[j]);
+    if (lane == 0) {
+        if (ALL_H) {
+#pragma unroll
+            for (int j = 0; j < K * (K + 1) / 2; j++) acc_sm->H[j] = H[j];
+        }
+        if (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_GRAD) {
+#pragma unroll
+            for (int j = 0; j < K; j++) acc_sm->g[j] = xty[j] - H[j];
+        }
+        if (MODE == PASS_FULL || MODE == PASS_LL) {
+            double s = -H[0];
+#pragma unroll
+            for (int j = 0; j < K; j++) s = fma(beta[j], xty[j], s);
+            acc_sm->ll = s;
+        } else {
+            acc_sm->ll = 0.0;
+        }
+        acc_sm->bad = 0;
+        acc_sm->has_gl = 0;
+    }
+    return true;
+}
+
+// Binomial child with an intercept, either method (see warp_pass_bin for the identities; the Bayes log term
+// uses sum log(1+E) = sum log(1+e) + beta'(X'1)). false: some eta outside the range the fast row op is exact
+// for - mle: eta >= 12 (rho rows) or <= -354.89; bayes: |eta| >= 700; NaN either way.
+template <int KIND, int K, int MODE>
+__device__ __forceinline__ bool lean_pass_bin(const double *const (&cp)[MAXK], const double *beta_sm, const double *xty,
+                                              const double *xt1, long long n, const RowConst rc, const double *tab256,
+                                              PassAcc *acc_sm, double *tile)
+{
+    constexpr int KD = K - 1;
+    constexpr int KDA = KD > 0 ? KD : 1;
+    constexpr bool NEED_H = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_HESS);
+    constexpr bool NEED_G = (MODE == PASS_FULL || MODE == PASS_HG || MODE == PASS_GRAD);
+    constexpr bool NEED_L = (MODE == PASS_FULL || MODE == PASS_LL);
+    constexpr bool MLE_ = (KIND == RK_BIN_MLE);
+    constexpr int NHA = NEED_H ? K * (K + 1) / 2 : 1;
+    const int lane = threadIdx.x & 31;
+    double beta[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) beta[j] = beta_sm[j];
+    double H[NHA], S[K], L = 0.0;
+#pragma unroll
+    for (int j = 0; j < NHA; j++) H[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; j++) S[j] = 0.0;
+    RowTrack tk = row_track_init();
+    auto row = [&](const double (&x)[KDA]) -> int {
+        double eta = beta[0];
+#pragma unroll
+        for (int j = 0; j < KD; j++) eta = fma(x[j], beta[j + 1], eta);
+        const double e = fast_exp256(-eta, tab256);
+        const double d = 1.0 + e;
+        if (NEED_L) L += fast_log_ge1(d, rc.logtab);
+        if (NEED_H || NEED_G) {
+            const double g = fast_rcp_approx(d);
+            if (NEED_H) {
+                const double w = fma(-g, g, g);
+                H[0] += w;
+                int t = 1;
+#pragma unroll
+                for (int q = 0; q < KD; q++) { H[t] = fma(w, x[q], H[t]); t++; }
+#pragma unroll
+                for (int p = 0; p < KD; p++) {
+                    const double wx = w * x[p];
+#pragma unroll
+                    for (int q = p; q < KD; q++) { H[t] = fma(wx, x[q], H[t]); t++; }
+                }
+            }
+            if (NEED_G) {
+                S[0] += g;
+#pragma unroll
+                for (int q = 0; q < KD; q++) S[q + 1] = fma(g, x[q], S[q + 1]);
+            }
+        }
+        return hi_word(eta);
+    };
+    lean_stream<KD>(cp, n, tile, tk, row);
+    const int out_of_range = MLE_ ? ((tk.smax >= 0x40280000) | (tk.umax >= 0xC0762E42u))
+                                  : ((tk.smax >= 0x4085E000) | (tk.umax >= 0xC085E000u));
+    if (__any_sync(0xffffffffu, out_of_range)) return false;
+    if (NEED_H) {
+#pragma unroll
+        for (int j = 0; j < NHA; j++) H[j] = warp_sum(H[j]);
+    }
+    if (NEED_G) {
+#pragma unroll
+        for (int j = 0; j < K; j++) S[j] = warp_sum(S[j]);
+    }
+    if (NEED_L) L = warp_sum(L);
+    if (lane == 0) {
+        if (NEED_H) {
+#pragma unroll
+            for (int j = 0; j < NHA; j++) acc_sm->H[j] = H[j];
+        }
+        if (NEED_G) {
+            const double dbp = rc.bp1 - rc.bp0;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                acc_sm->g[j] = MLE_ ? fma(dbp, xty[j], rc.bp0 * xt1[j]) - S[j] : xty[j] - S[j];
+                if (MLE_) acc_sm->gl[j] = xty[j] - S[j];
+            }
+        }
+        double ll = 0.0;
+        if (NEED_L) {
+            ll = -L;
+#pragma unroll
+            for (int j = 0; j < K; j++) ll = fma(beta[j], xty[j] - xt1[j], ll);
+        }
+        acc_sm->ll = ll;
+        acc_sm->bad = 0;
+        acc_sm->has_gl = (MLE_ && NEED_G) ? 1 : 0;
+    }
+    return true;
+}
+
 template <int KIND, int K, bool ICPT, int MODE>
 __device__ __forceinline__ void run_pass(const double *__restrict__ y, const double *const (&cp)[MAXK],
                                          const double *beta_sm, long long n, const RowConst rc, PassAcc *acc_sm,
-                                         double *tile, const double *xty)
+                                         double *tile, const double *xty, const double *tab256, int &careful)
 {
+#if ABN_LEAN
+    if (ICPT && !careful && KIND != RK_PINIT) {
+        bool ok;
+        if (KIND == RK_POIS) ok = lean_pass_pois<K, MODE>(cp, beta_sm, xty, n, tab256, acc_sm, tile);
+        else ok = lean_pass_bin<KIND == RK_BIN_MLE ? RK_BIN_MLE : RK_BIN_BAYES, K, MODE>(cp, beta_sm, xty, xty + MAXK, n, rc, tab256, acc_sm, tile);
+        if (ok) return;
+        careful = 1; // this fit leaves the range of the lean row ops: careful passes from here on
+    }
+#endif
 #if ABN_STAGE
     if (KIND == RK_POIS && ICPT) {
         warp_pass_pois<K, MODE>(cp, beta_sm, xty, n, rc, acc_sm, tile);
@@ -624,15 +902,17 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
     __shared__ double exp_tab[ABN_EXP2_N];
     __shared__ double lnmu_tab[64];
     __shared__ double log_tab[128];
+    __shared__ double exp256_tab[ABN_EXP256_N]; // pre-scaled 2^(j/256) (fast_exp256, lean passes)
     if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
-    extern __shared__ double stage_tiles[]; // FIT_WARPS x FIT_STAGES x (KD+1) x 32 FIT_UNROLL (staged pass)
+    extern __shared__ __align__(16) double stage_tiles[]; // FIT_WARPS x fit_stage_doubles_per_warp
     if (threadIdx.x < ABN_EXP2_N) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
+    for (int j = threadIdx.x; j < ABN_EXP256_N; j += FIT_WARPS * 32) exp256_tab[j] = exp256_entry(c_exp2_256_table[j], j);
     if (KIND == RK_POIS && threadIdx.x < 64) lnmu_tab[threadIdx.x] = log((double)threadIdx.x + 0.1);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FitState &st = st_all[warp];
     PassAcc *acc = &acc_all[warp];
-    double *tile = stage_tiles + (size_t)warp * FIT_STAGES * (K - (ICPT ? 1 : 0) + 1) * 32 * FIT_UNROLL;
+    double *tile = stage_tiles + (size_t)warp * fit_stage_doubles_per_warp<K, ICPT>();
     double *xty = xty_all[warp];
 
     for (;;) {
@@ -680,14 +960,15 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
         }
         mode = __shfl_sync(0xffffffffu, mode, 0);
         __syncwarp();
+        int careful = 0; // set by the first lean pass that meets an eta outside its range (run_pass)
         while (mode != PASS_DONE) {
             // only the modes a row kind's state machines can ask for are instantiated
-            if (mode == PASS_HG) run_pass<KIND, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty);
-            else if (mode == PASS_FULL) run_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc, tile, xty);
-            else if (mode == PASS_LL) run_pass<KIND, K, ICPT, PASS_LL>(y, cp, st.x, m.n, rc, acc, tile, xty);
-            else if (KIND != RK_BIN_MLE && mode == PASS_GRAD) run_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc, tile, xty);
-            else if (KIND != RK_BIN_MLE && mode == PASS_HESS) run_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc, tile, xty);
-            else if (KIND == RK_POIS && mode == PASS_PINIT) run_pass<RK_PINIT, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty);
+            if (mode == PASS_HG) run_pass<KIND, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
+            else if (mode == PASS_FULL) run_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
+            else if (mode == PASS_LL) run_pass<KIND, K, ICPT, PASS_LL>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
+            else if (KIND != RK_BIN_MLE && mode == PASS_GRAD) run_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
+            else if (KIND != RK_BIN_MLE && mode == PASS_HESS) run_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
+            else if (KIND == RK_POIS && mode == PASS_PINIT) run_pass<RK_PINIT, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
             __syncwarp();
             if (lane == 0) mode = fit_consume(st, c, *acc);
             mode = __shfl_sync(0xffffffffu, mode, 0);
@@ -711,20 +992,32 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
 }
 
 // host-side launcher table entry
-typedef void (*FitLaunchFn)(const DataMeta &, const Control &, const FitDesc *, const int *, const int *, int,
-                            int *, ResultPtrs, int grid, cudaStream_t);
+typedef cudaError_t (*FitLaunchFn)(const DataMeta &, const Control &, const FitDesc *, const int *, const int *, int,
+                                   int *, ResultPtrs, int grid, cudaStream_t);
+
+// the opt-in to more than 48 KB of dynamic shared memory is a per-device attribute of the kernel: it is
+// set once per (instantiation, device) - a process may score on several devices (abn_control.devices)
+inline bool first_launch_on_device(bool (&done)[64])
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
 
 template <int KIND, int K, bool ICPT>
-void launch_fit(const DataMeta &m, const Control &c, const FitDesc *descs, const int *child, const int *list,
-                int count, int *counter, ResultPtrs out, int grid, cudaStream_t stream)
+cudaError_t launch_fit(const DataMeta &m, const Control &c, const FitDesc *descs, const int *child, const int *list,
+                       int count, int *counter, ResultPtrs out, int grid, cudaStream_t stream)
 {
     constexpr size_t smem = fit_stage_bytes<K, ICPT>();
-    static bool configured = false; // one attribute call per instantiation and process
-    if (!configured && smem > 0) {
-        cudaFuncSetAttribute(fit_kernel<KIND, K, ICPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+    static bool configured[64] = {false};
+    if (smem > 0 && first_launch_on_device(configured)) {
+        cudaError_t e = cudaFuncSetAttribute(fit_kernel<KIND, K, ICPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
     }
     fit_kernel<KIND, K, ICPT><<<grid, FIT_WARPS * 32, smem, stream>>>(m, c, descs, child, list, count, counter, out);
+    return cudaGetLastError();
 }
 
 // defined in fit_bin_mle.cu / fit_bin_bayes.cu / fit_pois.cu: [k][icpt]

@@ -101,7 +101,7 @@ fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ des
     if (threadIdx.x < ABN_EXP2_N) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
     if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
     __syncthreads();
-    extern __shared__ double stage_tiles[];
+    extern __shared__ __align__(16) double stage_tiles[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     MnState &st = st_all[warp];
     MnAcc *acc = &acc_all[warp];
@@ -147,20 +147,21 @@ fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ des
     }
 }
 
-typedef void (*MnLaunchFn)(const DataMeta &, const Control &, const FitDesc *, const int *, int, int *, ResultPtrs,
-                           int grid, cudaStream_t);
+typedef cudaError_t (*MnLaunchFn)(const DataMeta &, const Control &, const FitDesc *, const int *, int, int *, ResultPtrs,
+                                  int grid, cudaStream_t);
 
 template <int L, int K, bool ICPT>
-void launch_mn(const DataMeta &m, const Control &c, const FitDesc *descs, const int *list, int count, int *counter,
-               ResultPtrs out, int grid, cudaStream_t stream)
+cudaError_t launch_mn(const DataMeta &m, const Control &c, const FitDesc *descs, const int *list, int count, int *counter,
+                      ResultPtrs out, int grid, cudaStream_t stream)
 {
     constexpr size_t smem = mn_stage_bytes<L, K, ICPT>();
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(fit_mn_kernel<L, K, ICPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+    static bool configured[64] = {false}; // per device, see launch_fit
+    if (first_launch_on_device(configured)) {
+        cudaError_t e = cudaFuncSetAttribute(fit_mn_kernel<L, K, ICPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
     }
     fit_mn_kernel<L, K, ICPT><<<grid, MN_WARPS * 32, smem, stream>>>(m, c, descs, list, count, counter, out);
+    return cudaGetLastError();
 }
 
 MnLaunchFn get_launch_mn(int L, int k, int icpt); // fit_table.cu

@@ -237,11 +237,13 @@ cudaError_t abn_wide_launch(const abnc::DataMeta &m, const abnc::Control &c, con
 {
     using namespace ABN_NS;
     const size_t smem = sizeof(WideShared);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false}; // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(fit_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int grid = std::min(count, sm_count * 4);
     fit_wide_kernel<<<grid, 32, smem, stream>>>(m, c, child, parents, width, list, count, counter, out);

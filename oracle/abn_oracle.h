@@ -69,6 +69,10 @@ void or_mle_poisson(const double *X, const double *y, long n, int k, int maxit, 
  * R/build_score_cache_mle.R:319-331; ycode[i] in 0..L-1; R = rank(X) enters edf */
 void or_mle_multinomial(const double *X, const int *ycode, long n, int k, int L, int R,
                         or_fit *out);
+/* test knob: row order of every sum over the observations (0 ascending, 1 descending), see mle.c */
+void or_set_sum_order(int order);
+extern int or_sum_order_;
+#define OR_ROWS(i, n) for (long c_ = 0, i = (or_sum_order_ ? (long)(n) - 1 : 0); c_ < (long)(n); c_++, i += (or_sum_order_ ? -1 : 1))
 int or_rank_cpp(const double *X, long n, int k);                                      /* src/rank.cpp:15 */
 
 /* Bayes Laplace: X column-major n x m INCLUDING the intercept (build_designmatrix*).

@@ -21,11 +21,11 @@ typedef struct lap {
 
 static void eta_of(const lap *L, const double *beta)
 {
-    for (long i = 0; i < L->n; i++) L->eta[i] = 0.0;
+    OR_ROWS(i, L->n) L->eta[i] = 0.0;
     for (int a = 0; a < L->m; a++) {
         const double *xa = L->X + (size_t)a * L->n;
         double c = beta[a];
-        for (long i = 0; i < L->n; i++) L->eta[i] += xa[i] * c;
+        OR_ROWS(i, L->n) L->eta[i] += xa[i] * c;
     }
 }
 
@@ -50,8 +50,8 @@ static double lap_g(lap *L, const double *th)
     eta_of(L, th);
     if (L->family == ABN_BINOMIAL) {                      /* node_binomial.c:585-649 */
         double t1 = 0.0, s = 0.0;
-        for (long i = 0; i < n; i++) t1 += L->y[i] * L->eta[i];
-        for (long i = 0; i < n; i++) {
+        OR_ROWS(i, n) t1 += L->y[i] * L->eta[i];
+        OR_ROWS(i, n) {
             double big = exp(L->eta[i]);
             s += (big != INFINITY) ? -log(1.0 + big) : -L->eta[i]; /* :633-639 */
         }
@@ -59,14 +59,14 @@ static double lap_g(lap *L, const double *th)
     }
     if (L->family == ABN_POISSON) {                       /* node_poisson.c:517-571 */
         double t1 = 0.0, s = 0.0;
-        for (long i = 0; i < n; i++) t1 += L->y[i] * L->eta[i];
-        for (long i = 0; i < n; i++) s += -lgamma(L->y[i] + 1.0) - exp(L->eta[i]); /* gsl_sf_lnfact :561 */
+        OR_ROWS(i, n) t1 += L->y[i] * L->eta[i];
+        OR_ROWS(i, n) s += -lgamma(L->y[i] + 1.0) - exp(L->eta[i]); /* gsl_sf_lnfact :561 */
         return (-1.0 / dn) * (t1 + s + prior_terms(L, th));
     }
     /* Gaussian, node_gaussian.c:503-579 */
     double tau = th[L->m];
     double yxb = 0.0, xbxb = 0.0, yy = 0.0;
-    for (long i = 0; i < n; i++) {
+    OR_ROWS(i, n) {
         yxb += L->y[i] * L->eta[i];
         xbxb += L->eta[i] * L->eta[i];
         yy += L->y[i] * L->y[i];
@@ -90,23 +90,23 @@ static void lap_dg(lap *L, const double *th, double *dg)
     for (int a = 0; a < m; a++) {
         const double *xa = L->X + (size_t)a * n;
         double s = 0.0;
-        for (long i = 0; i < n; i++) s += xa[i] * L->y[i];
+        OR_ROWS(i, n) s += xa[i] * L->y[i];
         xty[a] = s;
     }
     if (L->family == ABN_BINOMIAL) {                      /* node_binomial.c:655-719 */
-        for (long i = 0; i < n; i++) {
+        OR_ROWS(i, n) {
             double big = exp(L->eta[i]);
             L->wrk[i] = (big != INFINITY) ? -big / (1 + big) : -1.0; /* :697-700 */
         }
     } else if (L->family == ABN_POISSON) {                /* node_poisson.c:576-630 */
-        for (long i = 0; i < n; i++) L->wrk[i] = -exp(L->eta[i]);
+        OR_ROWS(i, n) L->wrk[i] = -exp(L->eta[i]);
     } else {                                              /* node_gaussian.c:586-654 */
-        for (long i = 0; i < n; i++) L->wrk[i] = -L->eta[i];
+        OR_ROWS(i, n) L->wrk[i] = -L->eta[i];
     }
     for (int a = 0; a < m; a++) {
         const double *xa = L->X + (size_t)a * n;
         double s = 0.0;
-        for (long i = 0; i < n; i++) s += xa[i] * L->wrk[i];
+        OR_ROWS(i, n) s += xa[i] * L->wrk[i];
         xtr[a] = s;
     }
     if (L->family == ABN_GAUSSIAN) {
@@ -116,7 +116,7 @@ static void lap_dg(lap *L, const double *th, double *dg)
             dg[a] = (-1.0 / dn) * (prior + tau * (xty[a] + xtr[a]));             /* :625-637 */
         }
         double rss = 0.0;
-        for (long i = 0; i < n; i++) { double e = L->y[i] - L->eta[i]; rss += e * e; }
+        OR_ROWS(i, n) { double e = L->y[i] - L->eta[i]; rss += e * e; }
         dg[m] = (-1.0 / dn) * ((dn / (2.0 * tau)) + rss * (-0.5) + (L->gshape - 1.0) / tau
                                - (1.0 / L->gscale));                             /* :645-651 */
     } else {
@@ -141,7 +141,7 @@ static void lap_hess(lap *L, const double *th, double *H)
             for (int k = 0; k < m; k++) {
                 const double *xj = L->X + (size_t)j * n, *xk = L->X + (size_t)k * n;
                 double s = 0.0;
-                for (long i = 0; i < n; i++) s += xj[i] * xk[i];
+                OR_ROWS(i, n) s += xj[i] * xk[i];
                 H[j * M + k] = (j != k) ? (-1.0 / dn) * (-tau * s)
                                         : (-1.0 / dn) * (-tau * s - 1.0 / (L->psd * L->psd)); /* :700-709 */
             }
@@ -150,26 +150,26 @@ static void lap_hess(lap *L, const double *th, double *H)
         for (int j = 0; j < m; j++) {
             const double *xj = L->X + (size_t)j * n;
             double s = 0.0;
-            for (long i = 0; i < n; i++) s += xj[i] * (L->y[i] - L->eta[i]);
+            OR_ROWS(i, n) s += xj[i] * (L->y[i] - L->eta[i]);
             H[m * M + j] = H[j * M + m] = (-1.0 / dn) * s;                        /* :718-735 */
         }
         return;
     }
     if (L->family == ABN_BINOMIAL) {                      /* node_binomial.c:759-770 */
-        for (long i = 0; i < n; i++) {
+        OR_ROWS(i, n) {
             double t1 = L->eta[i];
             double t2 = -2.0 * log(1 + exp(L->eta[i])) - log(dn);
             double v = exp(t1 + t2);
             L->wrk[i] = isnan(v) ? 0.0 : v;
         }
     } else {                                              /* node_poisson.c:665-667 */
-        for (long i = 0; i < n; i++) L->wrk[i] = exp(L->eta[i]) / dn;
+        OR_ROWS(i, n) L->wrk[i] = exp(L->eta[i]) / dn;
     }
     for (int j = 0; j < m; j++) {
         for (int k = 0; k < m; k++) {
             const double *xj = L->X + (size_t)j * n, *xk = L->X + (size_t)k * n;
             double s = 0.0;
-            for (long i = 0; i < n; i++) s += (xj[i] * xk[i]) * L->wrk[i];
+            OR_ROWS(i, n) s += (xj[i] * xk[i]) * L->wrk[i];
             if (j == k) s += 1.0 / (dn * L->psd * L->psd);  /* node_binomial.c:781-789 */
             H[j * M + k] = s;
         }
@@ -189,7 +189,7 @@ static void lap_inits(lap *L, double *th)
         for (int k = 0; k < m; k++) {
             const double *xj = L->X + (size_t)j * n, *xk = L->X + (size_t)k * n;
             double s = 0.0;
-            for (long i = 0; i < n; i++) s += xj[i] * xk[i];
+            OR_ROWS(i, n) s += xj[i] * xk[i];
             XtX[j * m + k] = s;
         }
     or_lu_decomp(XtX, m, perm, &sg);
@@ -200,9 +200,9 @@ static void lap_inits(lap *L, double *th)
             const double *xj = L->X + (size_t)j * n;
             double s = 0.0;
             if (L->family == ABN_POISSON)
-                for (long i = 0; i < n; i++) s += xj[i] * log(L->y[i] + 0.1);   /* node_poisson.c:743 */
+                OR_ROWS(i, n) s += xj[i] * log(L->y[i] + 0.1);   /* node_poisson.c:743 */
             else
-                for (long i = 0; i < n; i++) s += xj[i] * L->y[i];
+                OR_ROWS(i, n) s += xj[i] * L->y[i];
             xty[j] = s;
         }
         for (int j = 0; j < m; j++) {
@@ -219,7 +219,7 @@ static void lap_inits(lap *L, double *th)
          * scratch vector; we use the coefficients just set (unpinned corner). */
         eta_of(L, err ? th : b);
         double rss = 0.0;
-        for (long i = 0; i < n; i++) { double e = L->y[i] - L->eta[i]; rss += e * e; }
+        OR_ROWS(i, n) { double e = L->y[i] - L->eta[i]; rss += e * e; }
         th[m] = 1.0 / (rss / ((double)n - (double)m));
     }
     L->passes++;

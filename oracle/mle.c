@@ -7,23 +7,31 @@
 #include "abn_oracle.h"
 #include "linalg.h"
 
+/* Summation order of the Gram products. The reference leaves it to the BLAS behind Armadillo (blocked,
+ * vectorised, platform dependent); 0 = ascending rows (default), 1 = descending rows. The tests use 1 to tell
+ * fits whose result depends on that order - rounding-noise-driven near-separation fits, which the reference
+ * itself does not reproduce across BLAS builds - from genuine parity failures. */
+int or_sum_order_ = 0;
+void or_set_sum_order(int order) { or_sum_order_ = order; }
+
 /* A.t() * (W % A.each_col()) and A.t() * (W % z), X column-major n x k; w == NULL means 1 */
 static void weighted_gram(const double *X, long n, int k, const double *w, const double *z,
                           double *G, double *rhs)
 {
+    const long i0 = or_sum_order_ ? n - 1 : 0, di = or_sum_order_ ? -1 : 1;
     for (int a = 0; a < k; a++) {
         const double *xa = X + (size_t)a * n;
         for (int b = a; b < k; b++) {
             const double *xb = X + (size_t)b * n;
             double s = 0.0;
-            if (w) for (long i = 0; i < n; i++) s += xa[i] * (w[i] * xb[i]);
-            else   for (long i = 0; i < n; i++) s += xa[i] * xb[i];
+            if (w) for (long c = 0, i = i0; c < n; c++, i += di) s += xa[i] * (w[i] * xb[i]);
+            else   for (long c = 0, i = i0; c < n; c++, i += di) s += xa[i] * xb[i];
             G[a * k + b] = G[b * k + a] = s;
         }
         if (rhs) {
             double s = 0.0;
-            if (w) for (long i = 0; i < n; i++) s += xa[i] * (w[i] * z[i]);
-            else   for (long i = 0; i < n; i++) s += xa[i] * z[i];
+            if (w) for (long c = 0, i = i0; c < n; c++, i += di) s += xa[i] * (w[i] * z[i]);
+            else   for (long c = 0, i = i0; c < n; c++, i += di) s += xa[i] * z[i];
             rhs[a] = s;
         }
     }

@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
                                  C.POINTER(capi.Result), C.c_int]
     L.or_score_cache.restype = C.c_int
     L.or_num_threads.restype = C.c_int
+    L.or_set_sum_order.argtypes = [C.c_int]
+    L.or_set_sum_order.restype = None
     _lib = L
     return L
 
@@ -189,6 +191,11 @@ def score_cache(X, node_family, node_col0, child, parents, control: capi.Control
         raise RuntimeError(f"or_score_cache failed: {rc}")
     del keep1, keep2
     return arrs
+
+
+def set_sum_order(order: int) -> None:
+    """Test knob: row order of the Gram sums (0 ascending, 1 descending) - the reference leaves it to its BLAS."""
+    lib().or_set_sum_order(int(order))
 
 
 def num_threads() -> int:

@@ -254,3 +254,12 @@ extern "C" void sim_fast_exp(const double *t, double *out, long n)
 {
     for (long i = 0; i < n; i++) out[i] = fast_exp(t[i], h_exp2_table);
 }
+
+// the lean passes' exp: 256-entry pre-scaled table (fastmath.cuh fast_exp256)
+extern "C" void sim_fast_exp256(const double *t, double *out, long n)
+{
+    static double tab[ABN_EXP256_N];
+    static bool done = false;
+    if (!done) { for (int j = 0; j < ABN_EXP256_N; j++) tab[j] = exp256_entry(h_exp2_256_table[j], j); done = true; }
+    for (long i = 0; i < n; i++) out[i] = fast_exp256(t[i], tab);
+}

@@ -202,7 +202,7 @@ def test_mle_shortcuts_on_small_and_strongly_dependent_data():
     oracle, which iterates exactly like the reference: small n, strong effects, unscaled count parents."""
     rng = np.random.default_rng(7)
     fams = ["binomial", "poisson", "gaussian", "binomial", "poisson", "gaussian"]
-    worst, compared = 0.0, 0
+    worst, compared, n_chaotic = 0.0, 0, 0
     for n, scale in [(40, 2.5), (80, 1.0), (150, 2.5), (400, 0.3), (1500, 1.0), (6000, 2.5)]:
         z = rng.standard_normal((n, 3))
         data, dists = {}, {}
@@ -223,11 +223,15 @@ def test_mle_shortcuts_on_small_and_strongly_dependent_data():
         par = H.parents_from_node_defn(nd, 3)
         ctrl = H.control("mle", d)
         sim = H.sim_score(P, ch.astype(np.int32), par, ctrl)
-        ref = H.oracle_score(P, ch.astype(np.int32), par, ctrl)
-        ok = (ref["status"] == 0) & (sim["status"] == 0) & np.isfinite(ref["mlik"])
-        # flags may differ only for fits the reference itself needs > 50 iterations on (near separation)
-        differ = sim["status"] != ref["status"]
-        assert (ref["iters"][differ] > 50).all()
+        # Flags must be identical, and values within 1e-9, on every row whose reference result is defined: the
+        # exceptions are the rows on which the oracle disagrees WITH ITSELF when its Gram sums run over the
+        # rows in the opposite order (near-separated binomial fits at the iteration cap: differences of
+        # 5e-7 .. 2e-3 and flipped flags between two legal summation orders of the reference's BLAS).
+        chaotic, ref, _ = H.oracle_order_sensitive(P, ch.astype(np.int32), par, ctrl)
+        n_chaotic += int(chaotic.sum())
+        assert (sim["status"] == ref["status"])[~chaotic].all()
+        assert (ref["iters"][chaotic] > 15).all()
+        ok = ~chaotic & (ref["status"] == 0) & np.isfinite(ref["mlik"])
         rel = H.rel_err(sim["mlik"], ref["mlik"])
         worst = max(worst, rel[ok].max())
         compared += int(ok.sum())
@@ -235,6 +239,7 @@ def test_mle_shortcuts_on_small_and_strongly_dependent_data():
         pois = ok & (fam == capi.POISSON)
         assert sim["iters"][pois].mean() < ref["iters"][pois].mean()
     assert compared > 800 and worst < 1e-9, (compared, worst)
+    assert 0 < n_chaotic < 20  # the fuzz case of round 1 (n = 40, child v3) is in this set
 
 
 @pytest.mark.parametrize("method", ["mle", "bayes"])
