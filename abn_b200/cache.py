@@ -221,6 +221,9 @@ def kernel_name(kid: int) -> str:
         return "fit_wide_kernel"
     if kid == 1:
         return "gauss_kernel"
+    cell0 = 2 + 6 * (capi.FAST_K + 1) * 2  # plan.cuh CELL_BUCKET0
+    if kid >= cell0:
+        return f"fit_cell_kernel<{('binomial', 'poisson')[kid - cell0]}>"
     code = kid - 2
     icpt, fk = code & 1, code >> 1
     fam, k = divmod(fk, capi.FAST_K + 1)

@@ -19,6 +19,7 @@
 #include "../../include/abn_b200.h"
 #include "fit_kernel.cuh"
 #include "fit_mn_kernel.cuh"
+#include "fit_cell.cuh"
 
 using namespace abn;
 
@@ -27,6 +28,10 @@ cudaError_t abn_wide_launch(const abnc::DataMeta &m, const abnc::Control &c, con
                             int width, const int *list, int count, int *counter, abnc::ResultPtrs out, int sm_count,
                             cudaStream_t stream);
 int abn_wide_max_k();
+// fit_cell.cu: all-discrete designs on contingency tables (kind: RK_BIN_MLE, RK_POIS, RK_BIN_BAYES)
+cudaError_t abn_cell_launch(int kind, const abnc::DataMeta &m, const abnc::Control &c, const abn::FitDesc *descs,
+                            const int *child, const int *list, int count, int *counter, abnc::ResultPtrs out,
+                            int sm_count, cudaStream_t stream);
 
 static_assert(ABN_FAST_K == MAXK, "include/abn_b200.h and solver.cuh disagree on the fast-path design width");
 static_assert(MN_MAXL == MN_MAXL_, "plan.cuh and solver_mn.cuh disagree on the multinomial level limit");
@@ -229,9 +234,50 @@ __global__ void __launch_bounds__(256) lfact_kernel(const DataMeta m, double *__
 }
 
 // ---------------------------------------------------------------------------------------------
+// byte codes of the discrete columns (fit_cell.cuh): one pass over X at data_create. Every thread takes 16
+// consecutive rows of one column (128 bytes in, one 16-byte store out); a column counts as discrete when all
+// its values are integers in 0..255, and its cardinality is the largest code + 1.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+discretize_kernel(const double *__restrict__ X, long long ld, long long n, unsigned char *__restrict__ Xq, long long ldq,
+                  int *__restrict__ col_bad, int *__restrict__ col_max)
+{
+    const int col = blockIdx.y;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; // group of 16 rows
+    const long long r0 = g * 16;
+    int bad = 0, mx = 0;
+    if (r0 < n) {
+        const double *x = X + (long long)col * ld + r0;
+        unsigned w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const double v = (r0 + i < n) ? __ldg(x + i) : 0.0;
+            const int c = (v >= 0.0 && v <= 255.0) ? (int)v : 0;
+            bad |= ((double)c != v);
+            mx = max(mx, c);
+            w[i >> 2] |= (unsigned)c << (8 * (i & 3));
+        }
+        *reinterpret_cast<uint4 *>(Xq + (long long)col * ldq + r0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicOr(&col_bad[col], 1);
+        atomicMax(&col_max[col], mx);
+    }
+}
+
+__global__ void col_card_kernel(int n_cols, const int *__restrict__ col_bad, const int *__restrict__ col_max, int *__restrict__ col_card)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_cols) col_card[c] = col_bad[c] ? 0 : col_max[c] + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // design resolution: one thread per candidate
 // ---------------------------------------------------------------------------------------------
-__global__ void resolve_kernel(const DataMeta m, int method, long long rows, int width, const int *__restrict__ child,
+__global__ void resolve_kernel(const DataMeta m, int method, int flags, long long rows, int width, const int *__restrict__ child,
                                const int *__restrict__ parents, FitDesc *__restrict__ descs,
                                unsigned char *__restrict__ keys, int *__restrict__ idx)
 {
@@ -241,7 +287,9 @@ __global__ void resolve_kernel(const DataMeta m, int method, long long rows, int
     resolve_design(m, method, child[r], parents + r * width, width, d);
     if (d.k == 0 || (d.family == MULTINOMIAL && (d.nlev < 2 || d.nlev > MN_MAXL || method != MLE))) d.err = d.err ? d.err : 2;
     descs[r] = d;
-    keys[r] = (unsigned char)bucket_of(d);
+    int key = bucket_of(d);
+    if (cell_eligible(m, d, method, flags)) key = CELL_BUCKET0 + (d.family == POISSON ? 1 : 0);
+    keys[r] = (unsigned char)key;
     idx[r] = (int)r;
 }
 
@@ -314,6 +362,8 @@ struct abn_data {
     DataMeta m{};
     double *dX = nullptr, *dG = nullptr, *dLfact = nullptr;
     int *dFamily = nullptr, *dCol0 = nullptr, *dGwIndex = nullptr, *dPoisNode = nullptr;
+    unsigned char *dXq = nullptr; // byte codes of the discrete columns (fit_cell.cuh)
+    int *dColCard = nullptr;
     std::vector<int> family, col0, gw_index;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -350,6 +400,7 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
     free_scratch(d);
     dev_free(d->dX, d->stream); dev_free(d->dG, d->stream); dev_free(d->dLfact, d->stream); dev_free(d->dFamily, d->stream); dev_free(d->dCol0, d->stream);
     dev_free(d->dGwIndex, d->stream); dev_free(d->dPoisNode, d->stream);
+    dev_free(d->dXq, d->stream); dev_free(d->dColCard, d->stream);
     dev_free(d->dBucketStart, d->stream); dev_free(d->dCounters, d->stream);
     cudaStreamSynchronize(d->stream); // the frees above are stream-ordered
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -465,8 +516,15 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     TRY_OR_FREE(dev_alloc(&d->dCol0, (size_t)(ds->n_nodes + 1) * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dGwIndex, (size_t)ds->n_nodes * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dPoisNode, std::max<size_t>(1, pois_node.size()) * sizeof(int), d->stream));
-    TRY_OR_FREE(dev_alloc(&d->dBucketStart, (size_t)(NBUCKETS + 1) * sizeof(int), d->stream));
-    TRY_OR_FREE(dev_alloc(&d->dCounters, (size_t)(NBUCKETS + 1) * sizeof(int), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dBucketStart, (size_t)(NBUCKETS_ALL + 1) * sizeof(int), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dCounters, (size_t)(NBUCKETS_ALL + 1) * sizeof(int), d->stream));
+    // ABN_B200_NO_CELLS=1: every fit takes the streaming kernels (A/B runs, debugging)
+    const char *no_cells = std::getenv("ABN_B200_NO_CELLS");
+    const bool use_cells = !(no_cells && *no_cells && *no_cells != '0');
+    if (use_cells) {
+        TRY_OR_FREE(dev_alloc(&d->dXq, (size_t)ld * ds->n_cols, d->stream));
+        TRY_OR_FREE(dev_alloc(&d->dColCard, (size_t)ds->n_cols * 3 * sizeof(int), d->stream)); // card | bad | max
+    }
     tr.mark("create: streams + cudaMalloc");
     TRY_OR_FREE(cudaMemsetAsync(d->dX, 0, (size_t)ld * ds->n_cols * sizeof(double), d->stream));
     TRY_OR_FREE(cudaMemcpy2DAsync(d->dX, (size_t)ld * sizeof(double), ds->X, (size_t)ds->n * sizeof(double),
@@ -491,6 +549,27 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     d->m.node_gw = d->dGwIndex;
     d->m.n_pois = n_pois;
     d->m.pois_node = d->dPoisNode;
+    d->m.Xq = nullptr;
+    d->m.ldq = ld;
+    d->m.col_card = nullptr;
+    if (d->dXq) {
+        int *bad = d->dColCard + ds->n_cols, *mx = d->dColCard + 2 * ds->n_cols;
+        cudaError_t e = cudaMemsetAsync(d->dColCard, 0, (size_t)ds->n_cols * 3 * sizeof(int), d->stream);
+        if (e == cudaSuccess) {
+            const long long groups = (ds->n + 15) / 16;
+            discretize_kernel<<<dim3((unsigned)((groups + 255) / 256), ds->n_cols), 256, 0, d->stream>>>(d->dX, ld, ds->n, d->dXq, ld, bad, mx);
+            col_card_kernel<<<(ds->n_cols + 127) / 128, 128, 0, d->stream>>>(ds->n_cols, bad, mx, d->dColCard);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) {
+            rc = fail(err, errlen, ABN_ERR_CUDA, "discretize: %s", cudaGetErrorString(e));
+            abn_b200_data_destroy(d);
+            return rc;
+        }
+        d->timing.launches += 2;
+        d->m.Xq = d->dXq;
+        d->m.col_card = d->dColCard;
+    }
     rc = compute_gram(d, err, errlen);
     if (rc != ABN_OK) { abn_b200_data_destroy(d); return rc; }
     tr.mark("create: Gram + lfact");
@@ -588,23 +667,23 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     }
 
     const int tb = 128;
-    resolve_kernel<<<(unsigned)((rows + tb - 1) / tb), tb, 0, s>>>(d->m, c.method, rows, width, d->dChild, d->dParents,
+    resolve_kernel<<<(unsigned)((rows + tb - 1) / tb), tb, 0, s>>>(d->m, c.method, c.flags, rows, width, d->dChild, d->dParents,
                                                                   d->dDescs, d->dKeys, d->dIdx);
     KCHECK("resolve_kernel", s);
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(d->dSortTmp, d->sortTmpBytes, d->dKeys, d->dKeysSorted, d->dIdx, d->dIdxSorted,
                                              (int)rows, 0, 8, s));
-    CUDA_TRY(cudaMemsetAsync(d->dBucketStart, 0xff, (size_t)(NBUCKETS + 1) * sizeof(int), s));
-    CUDA_TRY(cudaMemsetAsync(d->dCounters, 0, (size_t)(NBUCKETS + 1) * sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(d->dBucketStart, 0xff, (size_t)(NBUCKETS_ALL + 1) * sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(d->dCounters, 0, (size_t)(NBUCKETS_ALL + 1) * sizeof(int), s));
     KCHECK("radix sort", s);
     bucket_bounds<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(d->dKeysSorted, rows, d->dBucketStart);
     KCHECK("bucket_bounds", s);
     launches += 3;
-    int hstart[NBUCKETS + 1];
+    int hstart[NBUCKETS_ALL + 1];
     CUDA_TRY(cudaMemcpyAsync(hstart, d->dBucketStart, sizeof(hstart), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
-    hstart[NBUCKETS] = (int)rows;
-    for (int b = NBUCKETS - 1; b >= 0; b--) if (hstart[b] < 0) hstart[b] = hstart[b + 1];
+    hstart[NBUCKETS_ALL] = (int)rows;
+    for (int b = NBUCKETS_ALL - 1; b >= 0; b--) if (hstart[b] < 0) hstart[b] = hstart[b + 1];
     CUDA_TRY(cudaEventRecord(ev[2], s));
 
     int n_unsupported = 0;
@@ -621,7 +700,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     for (auto &ss : d->side) CUDA_TRY(cudaStreamWaitEvent(ss, planned, 0));
     int n_side = 0;
     for (int pass = 0; pass < 2; pass++) {
-        for (int b = 0; b < NBUCKETS; b++) {
+        for (int b = 0; b < NBUCKETS_ALL; b++) {
             const int count = hstart[b + 1] - hstart[b];
             if (count <= 0) continue;
             // pass 0: the Gram-only Gaussian kernel (largest per-thread stack: launching it first
@@ -646,6 +725,9 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
                                          d->sm_count, ks));
             } else if (b == 1) {
                 gauss_kernel<<<(count + 127) / 128, 128, 0, ks>>>(d->m, c, d->dDescs, d->dChild, list, count, rp);
+            } else if (b >= CELL_BUCKET0) {
+                const int kind = (b == CELL_BUCKET0 + 1) ? RK_POIS : (c.method == MLE ? RK_BIN_MLE : RK_BIN_BAYES);
+                CUDA_TRY(abn_cell_launch(kind, d->m, c, d->dDescs, d->dChild, list, count, d->dCounters + b, rp, d->sm_count, ks));
             } else {
                 const int code = b - 2, icpt = code & 1, fk = code >> 1, fam = fk / (MAXK + 1), k = fk % (MAXK + 1);
                 FitLaunchFn fn = nullptr;
@@ -721,8 +803,9 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     d->timing.fit_ms = ms[2];
     d->timing.d2h_ms = ms[3];
     d->timing.launches = launches;
-    // algorithmic bytes: passes * n * (k_data + 1) * 8 per fit
-    auto fit_bytes = [&](long long r) {
+    // algorithmic bytes: passes * n * (k_data + 1) * 8 per streamed fit; a fit on a contingency table
+    // (fit_cell.cuh) reads its byte-coded columns once: n * (k_data + 1 for a binomial response)
+    auto fit_bytes = [&](long long r, bool cell) {
         int kd = 0;
         for (int j = 0; j < width; j++) {
             const int p = cand->parents[r * width + j];
@@ -730,22 +813,23 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
         }
         const int ch = cand->child[r];
         const int yw = d->col0[ch + 1] - d->col0[ch];
+        if (cell) return (long long)d->m.n * (kd + (d->family[ch] == ABN_BINOMIAL ? 1 : 0));
         return (long long)iters_dst[r] * d->m.n * (kd + yw) * 8;
     };
     long long bytes = 0;
-    for (long long r = 0; r < rows; r++) bytes += fit_bytes(r);
-    d->timing.algo_bytes = bytes;
     d->timing.n_kernels = (int)kid.size();
     for (size_t i = 0; i < kid.size(); i++) {
         float kms = 0;
         cudaEventElapsedTime(&kms, kev0[i], kev1[i]);
         long long kb = 0;
-        for (int t = 0; t < kcount[i]; t++) kb += fit_bytes(sorted_rows[kstart[i] + t]);
+        for (int t = 0; t < kcount[i]; t++) kb += fit_bytes(sorted_rows[kstart[i] + t], kid[i] >= CELL_BUCKET0);
+        bytes += kb;
         d->timing.kernel_id[i] = kid[i];
         d->timing.kernel_fits[i] = kcount[i];
         d->timing.kernel_bytes[i] = kb;
         d->timing.kernel_ms[i] = kms;
     }
+    d->timing.algo_bytes = bytes;
     for (auto &e : kev0) cudaEventDestroy(e);
     for (auto &e : kev1) cudaEventDestroy(e);
     for (auto &e : ev) cudaEventDestroy(e);

@@ -1,0 +1,30 @@
+// fit_cell.cu - the contingency-table kernels for all-discrete designs (fit_cell.cuh) and their launcher.
+#include <algorithm>
+
+#include "fit_cell.cuh"
+
+using namespace abn;
+
+template <int KIND>
+static cudaError_t launch_cell(const DataMeta &m, const Control &c, const FitDesc *descs, const int *child, const int *list,
+                               int count, int *counter, ResultPtrs out, int sm_count, cudaStream_t stream)
+{
+    constexpr size_t smem = (size_t)CELL_WARPS * (CELL_CAP + 32) * sizeof(unsigned);
+    static bool configured[64] = {false};
+    if (first_launch_on_device(configured)) {
+        cudaError_t e = cudaFuncSetAttribute(fit_cell_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int grid = std::min((count + CELL_WARPS - 1) / CELL_WARPS, sm_count * 2);
+    fit_cell_kernel<KIND><<<grid, CELL_WARPS * 32, smem, stream>>>(m, c, descs, child, list, count, counter, out);
+    return cudaGetLastError();
+}
+
+cudaError_t abn_cell_launch(int kind, const abnc::DataMeta &m, const abnc::Control &c, const abn::FitDesc *descs,
+                            const int *child, const int *list, int count, int *counter, abnc::ResultPtrs out,
+                            int sm_count, cudaStream_t stream)
+{
+    if (kind == RK_POIS) return launch_cell<RK_POIS>(m, c, descs, child, list, count, counter, out, sm_count, stream);
+    if (kind == RK_BIN_BAYES) return launch_cell<RK_BIN_BAYES>(m, c, descs, child, list, count, counter, out, sm_count, stream);
+    return launch_cell<RK_BIN_MLE>(m, c, descs, child, list, count, counter, out, sm_count, stream);
+}

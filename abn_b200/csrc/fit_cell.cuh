@@ -1,0 +1,386 @@
+// fit_cell.cuh - sufficient-statistic collapse for all-discrete designs: one warp per fit.
+//
+// When every design column of a binomial or Poisson child is discrete (integer codes 0..255: binomial
+// nodes, the one-hot columns of multinomial nodes, small counts), the linear predictor takes as many
+// values as there are distinct parent patterns ("cells"), and every sum a data pass produces,
+//     H = sum_i w(eta_i) x_i x_i',  g = sum_i r(eta_i, y_i) x_i,  ll = sum_i l(eta_i, y_i),
+// is the same sum over cells weighted by the cell counts. This is to discrete designs what the global
+// Gram matrix is to Gaussian children (plan.cuh): the warp builds the contingency table of the fit ONCE -
+// an integer pass over the byte-coded columns (DataMeta::Xq, 1 byte per value instead of 8, ~4 integer
+// instructions per row instead of ~40 mixed ones per row and pass) - and then runs the unchanged solver
+// state machine (solver.cuh) with passes over <= 4096 weighted cells instead of n rows.
+//
+//   binomial child (either method): cells over (y, parent pattern); each cell is one evaluation of the
+//       careful row op (RowOp<KIND>, rho always on) times its count - the reference's arithmetic per
+//       distinct row, no shortcuts (the passes cost nothing, so the fit iterates exactly as the reference
+//       does: solver.cuh sees has_gl = 0)
+//   Poisson child: cells over the parent pattern only; X'y comes from the global Gram matrix
+//       (g = X'y - sum N E x, ll = beta'X'y - sum N E, see warp_pass_pois)
+//
+// Table: the codes of the columns are packed into the cell index bit field by bit field (ceil(log2 card)
+// bits each, <= 10 bits in all); the warp's shared-memory table holds `copies` interleaved replicas of every
+// counter (copy = lane mod copies, 4096 / cells of them, at most 32): see cell_count_rows.
+// Counting is exact integer work, so the table - and with it every result - is independent of how the rows
+// are split over lanes: bit-identical under any partition of the candidate list.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "fit_kernel.cuh"
+
+namespace ABN_NS {
+
+constexpr int CELL_BITS = 12;             // log2 of the counters per warp
+constexpr int CELL_MAX_BITS = 10;         // widest cell index taken: at least 4 replicas per counter (<= 8 phases)
+constexpr int CELL_CAP = 1 << CELL_BITS;  // counters per warp
+constexpr int CELL_WARPS = 4;             // warps per CTA (16 KB of table each)
+
+// bits needed for codes 0 .. card-1
+ABN_HD int bits_for(int card)
+{
+    int b = 1;
+    while ((1 << b) < card) b++;
+    return b;
+}
+
+// Is this resolved design one the cell kernel takes? (called by resolve_kernel; host builds have no byte
+// codes and never say yes)
+ABN_HD bool cell_eligible(const DataMeta &m, const FitDesc &d, int method, int flags)
+{
+    if (m.col_card == nullptr || d.err || d.k < 1) return false;
+    if (d.family != BINOMIAL && d.family != POISSON) return false;
+    if (d.family == POISSON && method == MLE && (flags & 1)) return false; // the reference's start-value pass needs y per row
+    int bits = (d.family == BINOMIAL) ? 1 : 0;                             // the response is part of a binomial cell
+    for (int j = 0; j < d.k; j++) {
+        if (d.cols[j] < 0) continue;
+        const int card = m.col_card[d.cols[j]];
+        if (card <= 0) return false;
+        bits += bits_for(card);
+    }
+    if (d.family == BINOMIAL && m.col_card[d.ycol] != 2) return false;
+    return bits <= CELL_MAX_BITS;
+}
+
+struct CellPlan {
+    int ncol;            // byte columns that enter the cell index (binomial: the response first)
+    int col[MAXK + 1];   // stored column of each
+    int shift[MAXK + 1]; // bit position of its code in the cell index
+    int bits[MAXK + 1];
+    int total_bits;
+    int xslot[MAXK];     // design column j takes its value from byte column xslot[j] (-1: intercept)
+};
+
+// Contingency table of the fit: counter (cell << lc) | (lane & (copies - 1)) += 1 for every row, copies = 2^lc.
+// Shared-memory atomics cost ~2 cycles per LANE on this part (the load-store unit serialises them), so the
+// counters are plain read-modify-writes instead: with 32 replicas every lane owns its counters outright; with
+// fewer, the lanes that share a replica take turns (32 / copies phases separated by __syncwarp, each phase
+// conflict-free by construction).
+template <int NC>
+__device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPlan &cp, unsigned *tab, int lc)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned char *colp[NC];
+    int sh[NC];
+#pragma unroll
+    for (int j = 0; j < NC; j++) { colp[j] = m.Xq + (long long)cp.col[j] * m.ldq; sh[j] = cp.shift[j]; }
+    unsigned *const mine = tab + (lane & ((1 << lc) - 1));
+    const int nphase = 32 >> lc, my_phase = lane >> lc;
+    const long long n16 = m.n / 16;
+    const long long steps = (n16 + 31) / 32; // every lane runs the same number of steps (the phases synchronise)
+    // 16 rows per lane and step: one 16-byte load per column; the codes of 4 rows are combined at once when
+    // the whole index fits a byte (<= 256 cells), otherwise row by row
+    const bool bytewise = cp.total_bits <= 8;
+    for (long long st = 0; st < steps; st++) {
+        const long long c = st * 32 + lane;
+        const bool live = c < n16;
+        uint4 v[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) v[j] = live ? __ldg(reinterpret_cast<const uint4 *>(colp[j]) + c) : make_uint4(0u, 0u, 0u, 0u);
+        unsigned cells[16];
+        if (bytewise) {
+            unsigned w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                w[0] |= v[j].x << sh[j]; w[1] |= v[j].y << sh[j]; w[2] |= v[j].z << sh[j]; w[3] |= v[j].w << sh[j];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) cells[4 * q + b] = (w[q] >> (8 * b)) & 0xffu;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    unsigned cell = 0;
+#pragma unroll
+                    for (int j = 0; j < NC; j++) {
+                        const unsigned word = q == 0 ? v[j].x : (q == 1 ? v[j].y : (q == 2 ? v[j].z : v[j].w));
+                        cell |= ((word >> (8 * b)) & 0xffu) << sh[j];
+                    }
+                    cells[4 * q + b] = cell;
+                }
+            }
+        }
+        if (nphase == 1) {
+            if (live) {
+#pragma unroll
+                for (int r = 0; r < 16; r++) { unsigned *p = mine + (cells[r] << lc); *p = *p + 1u; }
+            }
+        } else {
+            // a dead lane (past the last full group of 16 rows) bumps a scratch counter beyond the table
+            unsigned *const dead = tab + CELL_CAP + lane;
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                unsigned *p = live ? mine + (cells[r] << lc) : dead;
+                for (int ph = 0; ph < nphase; ph++) {
+                    if (my_phase == ph) *p = *p + 1u;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    for (long long i0 = n16 * 16; i0 < m.n; i0 += 32) { // fewer than 16 rows left
+        const long long i = i0 + lane;
+        const bool live = i < m.n;
+        unsigned cell = 0;
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < NC; j++) cell |= (unsigned)__ldg(colp[j] + i) << sh[j];
+        }
+        unsigned *p = live ? mine + (cell << lc) : tab + CELL_CAP + lane;
+        for (int ph = 0; ph < nphase; ph++) {
+            if (my_phase == ph) *p = *p + 1u;
+            __syncwarp();
+        }
+    }
+}
+
+// one "data pass" over the cells. acc gets the same sums a row pass would produce.
+template <int KIND>
+__device__ __forceinline__ void cell_pass(const CellPlan &cp, const unsigned *cnt, int k, const double *beta_sm,
+                                          const double *xty, int mode, const RowConst rc, PassAcc *acc_sm)
+{
+    const int lane = threadIdx.x & 31;
+    const bool need_h = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_HESS);
+    const bool need_g = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_GRAD);
+    const bool need_l = (mode == PASS_FULL || mode == PASS_LL);
+    double beta[MAXK], H[NTRI], g[MAXK], ll = 0.0;
+#pragma unroll
+    for (int j = 0; j < MAXK; j++) { beta[j] = j < k ? beta_sm[j] : 0.0; g[j] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < NTRI; j++) H[j] = 0.0;
+    RowTrack tk = row_track_init();
+    const int ncell = 1 << cp.total_bits;
+    for (int c = lane; c < ncell; c += 32) {
+        const unsigned N = cnt[c];
+        if (N == 0) continue;
+        const double dn = (double)N;
+        double x[MAXK];
+        double eta = 0.0;
+#pragma unroll
+        for (int j = 0; j < MAXK; j++) {
+            x[j] = 0.0;
+            if (j < k) {
+                const int s = cp.xslot[j];
+                x[j] = s < 0 ? 1.0 : (double)((c >> cp.shift[s]) & ((1 << cp.bits[s]) - 1));
+                eta = fma(x[j], beta[j], eta);
+            }
+        }
+        double w = 0.0, r = 0.0, l = 0.0;
+        if (KIND == RK_POIS) {
+            row_track(tk, eta);
+            const double E = fast_exp(clamp_lo700(eta), rc.tab);
+            w = E; r = E; l = E; // r, l: the parts that are summed per cell; X'y is added below
+        } else {
+            const double y = (double)(c & 1); // the response is the first bit field of a binomial cell
+            RowOp<KIND>::template apply<true, true, true>(eta, y, rc, w, r, l, tk, true);
+        }
+        w *= dn; r *= dn; l *= dn;
+        if (need_h) {
+            int t = 0;
+#pragma unroll
+            for (int p = 0; p < MAXK; p++) {
+                const double wx = w * x[p];
+#pragma unroll
+                for (int q = p; q < MAXK; q++) { H[t] = fma(wx, x[q], H[t]); t++; }
+            }
+        }
+        if (need_g) {
+#pragma unroll
+            for (int p = 0; p < MAXK; p++) g[p] = fma(r, x[p], g[p]);
+        }
+        if (need_l) ll += l;
+    }
+    if (need_h) {
+#pragma unroll
+        for (int j = 0; j < NTRI; j++) H[j] = warp_sum(H[j]);
+    }
+    if (need_g) {
+#pragma unroll
+        for (int j = 0; j < MAXK; j++) g[j] = warp_sum(g[j]);
+    }
+    if (need_l) ll = warp_sum(ll);
+    const int bad = __any_sync(0xffffffffu, RowOp<KIND>::bad_of(tk));
+    if (lane == 0) {
+        // static register indices, run-time shared-memory addresses (the solver wants the packed k x k triangle)
+        if (need_h) {
+            int t = 0;
+#pragma unroll
+            for (int p = 0; p < MAXK; p++) {
+#pragma unroll
+                for (int q = p; q < MAXK; q++) {
+                    if (q < k) acc_sm->H[tri(p, q, k)] = H[t];
+                    t++;
+                }
+            }
+        }
+        if (need_g) {
+#pragma unroll
+            for (int j = 0; j < MAXK; j++)
+                if (j < k) acc_sm->g[j] = (KIND == RK_POIS) ? xty[j] - g[j] : g[j];
+        }
+        double lsum = 0.0;
+        if (need_l) {
+            if (KIND == RK_POIS) {
+                lsum = -ll;
+#pragma unroll
+                for (int j = 0; j < MAXK; j++)
+                    if (j < k) lsum = fma(beta[j], xty[j], lsum);
+            } else {
+                lsum = ll;
+            }
+        }
+        acc_sm->ll = lsum;
+        acc_sm->bad = bad;
+        acc_sm->has_gl = 0;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(CELL_WARPS * 32)
+fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ child,
+                const int *__restrict__ list, int count, int *counter, ResultPtrs out)
+{
+    __shared__ FitState st_all[CELL_WARPS];
+    __shared__ PassAcc acc_all[CELL_WARPS];
+    __shared__ CellPlan plan_all[CELL_WARPS];
+    __shared__ double xty_all[CELL_WARPS][MAXK];
+    __shared__ double exp_tab[ABN_EXP2_N];
+    __shared__ double log_tab[128];
+    extern __shared__ __align__(16) unsigned cell_tabs[]; // CELL_WARPS x (CELL_CAP counters + 32 scratch)
+    if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
+    if (threadIdx.x < ABN_EXP2_N) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FitState &st = st_all[warp];
+    PassAcc *acc = &acc_all[warp];
+    CellPlan &cp = plan_all[warp];
+    double *xty = xty_all[warp];
+    unsigned *tab = cell_tabs + (size_t)warp * (CELL_CAP + 32);
+
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(counter, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= count) break;
+        const int row = list[idx];
+        const FitDesc d = descs[row];
+        const int ch = child[row];
+        const int k = d.k;
+        if (lane == 0) {
+            int nc = 0, sh = 0;
+            if (d.family == BINOMIAL) { cp.col[0] = d.ycol; cp.shift[0] = 0; cp.bits[0] = 1; nc = 1; sh = 1; }
+            for (int j = 0; j < k; j++) {
+                if (d.cols[j] < 0) { cp.xslot[j] = -1; continue; }
+                const int b = bits_for(m.col_card[d.cols[j]]);
+                cp.col[nc] = d.cols[j]; cp.shift[nc] = sh; cp.bits[nc] = b;
+                cp.xslot[j] = nc;
+                nc++; sh += b;
+            }
+            cp.ncol = nc;
+            cp.total_bits = sh;
+            const long long gy = gram_col(d.ycol);
+            for (int j = 0; j < k; j++) xty[j] = m.G[(long long)gidx(d, j) * m.D + gy];
+        }
+        __syncwarp();
+        const int tb = cp.total_bits;
+        const int lc = min(5, CELL_BITS - tb); // log2 of the replicas per counter
+        for (int i = lane; i < (1 << (tb + lc)); i += 32) tab[i] = 0u;
+        __syncwarp();
+        switch (cp.ncol) {
+        case 0: break;
+        case 1: cell_count_rows<1>(m, cp, tab, lc); break;
+        case 2: cell_count_rows<2>(m, cp, tab, lc); break;
+        case 3: cell_count_rows<3>(m, cp, tab, lc); break;
+        case 4: cell_count_rows<4>(m, cp, tab, lc); break;
+        case 5: cell_count_rows<5>(m, cp, tab, lc); break;
+        case 6: cell_count_rows<6>(m, cp, tab, lc); break;
+        case 7: cell_count_rows<7>(m, cp, tab, lc); break;
+        case 8: cell_count_rows<8>(m, cp, tab, lc); break;
+        default: cell_count_rows<MAXK + 1>(m, cp, tab, lc); break;
+        }
+        __syncwarp();
+        // fold the replicas: counter of cell c ends up at tab[c]. Round r handles cells 32 r .. 32 r + 31: all
+        // reads of a round precede its writes, and later rounds read only beyond what has been written
+        if (cp.ncol == 0) {
+            if (lane == 0) tab[0] = (unsigned)m.n; // intercept-only Poisson fit: one cell
+        } else if (lc > 0) {
+            const int copies = 1 << lc;
+            for (int c0 = 0; c0 < (1 << tb); c0 += 32) {
+                const int cc = c0 + lane;
+                unsigned s = 0;
+                if (cc < (1 << tb))
+                    for (int r = 0; r < copies; r++) s += tab[(cc << lc) + r];
+                __syncwarp();
+                if (cc < (1 << tb)) tab[cc] = s;
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+
+        const RowConst rc = make_row_const((c.flags & 2) ? 0 : k, (double)m.n, exp_tab, log_tab, nullptr);
+        int mode = 0;
+        if (lane == 0) {
+            state_setup(m, d, ch, c, st);
+            if (c.method == BAYES) bayes_inits(m, d, ch, st);
+            mode = fit_begin(st, c);
+            if (KIND == RK_BIN_MLE) {
+                binomial_first_acc(m, d, *acc, !(c.flags & 2));
+                st.have_ll = 1;
+                mode = fit_consume(st, c, *acc);
+                st.passes--;
+            }
+            if (KIND == RK_POIS && mode == PASS_PINIT) {
+                poisson_init_acc(m, d, ch, *acc);
+                mode = fit_consume(st, c, *acc);
+                st.passes--;
+            }
+        }
+        mode = __shfl_sync(0xffffffffu, mode, 0);
+        __syncwarp();
+        while (mode != PASS_DONE) {
+            cell_pass<KIND>(cp, tab, k, st.x, xty, mode, rc, acc);
+            __syncwarp();
+            if (lane == 0) mode = fit_consume(st, c, *acc);
+            mode = __shfl_sync(0xffffffffu, mode, 0);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (out.mlik) out.mlik[row] = st.loglik;
+            if (c.method == MLE) {
+                if (out.aic) out.aic[row] = st.aic;
+                if (out.bic) out.bic[row] = st.bic;
+                if (out.mdl) out.mdl[row] = mdl_of(st.bic, d, c.nvars);
+            }
+            if (out.status) out.status[row] = st.status;
+            if (out.iters) out.iters[row] = st.passes;
+            write_coef(out, row, d, st.x, st.M);
+            write_se(out, row, d, st, c.method);
+            if (out.sse && c.method == MLE) out.sse[row] = sse_of(m, d, st.x);
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace ABN_NS

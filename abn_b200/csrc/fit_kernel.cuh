@@ -188,7 +188,10 @@ __device__ __forceinline__ void warp_pass(const double *__restrict__ y, const do
 constexpr int FIT_STAGES = 2;
 
 #ifndef ABN_LEAN_STAGES
-#define ABN_LEAN_STAGES 3
+#define ABN_LEAN_STAGES 2
+#endif
+#ifndef ABN_LEAN_DIRECT
+#define ABN_LEAN_DIRECT 0
 #endif
 // doubles of tile storage one warp needs: the staged pass (FIT_STAGES x (KD + 1) columns x 32 FIT_UNROLL rows)
 // or the lean pass (ABN_LEAN_STAGES x KD columns x 128 rows), whichever is larger
@@ -196,7 +199,7 @@ template <int K, bool ICPT>
 constexpr size_t fit_stage_doubles_per_warp()
 {
     const size_t staged = ABN_STAGE ? (size_t)FIT_STAGES * (K - (ICPT ? 1 : 0) + 1) * 32 * FIT_UNROLL : 0;
-    const size_t lean = ICPT ? (size_t)ABN_LEAN_STAGES * (K - 1) * 128 : 0;
+    const size_t lean = (ICPT && !ABN_LEAN_DIRECT) ? (size_t)ABN_LEAN_STAGES * (K - 1) * 128 : 0;
     return staged > lean ? staged : lean;
 }
 // bytes of dynamic shared memory the passes need per CTA
@@ -623,9 +626,6 @@ __device__ __forceinline__ void warp_pass_bin(const double *__restrict__ y, cons
 #ifndef ABN_LEAN
 #define ABN_LEAN 1
 #endif
-#ifndef ABN_LEAN_STAGES
-#define ABN_LEAN_STAGES 3
-#endif
 constexpr int LEAN_STAGES = ABN_LEAN_STAGES;
 constexpr int LEAN_TROWS = 128;
 
@@ -699,6 +699,75 @@ __device__ __forceinline__ void lean_stream(const double *const (&cp)[MAXK], lon
     }
 }
 
+#ifndef ABN_LEAN_DIRECT
+#define ABN_LEAN_DIRECT 0
+#endif
+// Variant without shared-memory staging: 16-byte read-only loads straight into registers. The two row pairs of
+// a 128-row tile live in two register sets; each set is reloaded with its rows of the NEXT tile right after the
+// pair has been computed, so a load has the compute time of the other pair (times the warps sharing the
+// scheduler) to arrive - more than the ~250-cycle L2 latency - and only one tile of registers is ever live.
+// Same row order as lean_stream, same bits. It halves the traffic through the SM's shared-memory / L1 data
+// pipe (128 B per cycle), which the staged variant saturates before the FP64 pipe for narrow designs.
+template <int KD, typename RowFn>
+__device__ __forceinline__ void lean_stream_direct(const double *const (&cp)[MAXK], long long n, RowTrack &tk, RowFn &&row)
+{
+    constexpr int TR = LEAN_TROWS;
+    constexpr int KDA = KD > 0 ? KD : 1;
+    const int lane = threadIdx.x & 31;
+    const int ntiles = (KD > 0) ? (int)(n / TR) : 0;
+    const double2 *base[KDA];
+#pragma unroll
+    for (int j = 0; j < KD; j++) base[j] = reinterpret_cast<const double2 *>(cp[j]) + lane;
+    double2 a[KDA], b[KDA];
+    if (ntiles > 0) {
+#pragma unroll
+        for (int j = 0; j < KD; j++) { a[j] = __ldg(base[j]); b[j] = __ldg(base[j] + 32); }
+    }
+    unsigned off = 0; // in double2 units: 64 per tile
+    for (int it = 0; it < ntiles; it++) {
+        const bool more = it + 1 < ntiles;
+        off += TR / 2;
+        double x0[KDA], x1[KDA];
+#pragma unroll
+        for (int j = 0; j < KD; j++) { x0[j] = a[j].x; x1[j] = a[j].y; }
+        const int h0 = row(x0), h1 = row(x1);
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < KD; j++) a[j] = __ldg(base[j] + off);
+        }
+        tk.smax = max(max(tk.smax, h0), h1);
+        tk.umax = max(max(tk.umax, (unsigned)h0), (unsigned)h1);
+#pragma unroll
+        for (int j = 0; j < KD; j++) { x0[j] = b[j].x; x1[j] = b[j].y; }
+        const int h2 = row(x0), h3 = row(x1);
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < KD; j++) b[j] = __ldg(base[j] + off + 32);
+        }
+        tk.smax = max(max(tk.smax, h2), h3);
+        tk.umax = max(max(tk.umax, (unsigned)h2), (unsigned)h3);
+    }
+    for (long long i = (long long)ntiles * TR + lane; i < n; i += 32) {
+        double xt[KDA];
+#pragma unroll
+        for (int j = 0; j < KD; j++) xt[j] = __ldg(cp[j] + i);
+        const int h = row(xt);
+        tk.smax = max(tk.smax, h);
+        tk.umax = max(tk.umax, (unsigned)h);
+    }
+}
+
+template <int KD, typename RowFn>
+__device__ __forceinline__ void lean_rows(const double *const (&cp)[MAXK], long long n, double *tile, RowTrack &tk, RowFn &&row)
+{
+#if ABN_LEAN_DIRECT
+    (void)tile;
+    lean_stream_direct<KD>(cp, n, tk, row);
+#else
+    lean_stream<KD>(cp, n, tile, tk, row);
+#endif
+}
+
 // Poisson with an intercept (see warp_pass_pois for the identities). false: eta left (-700, 700), nothing written.
 template <int K, int MODE>
 __device__ __forceinline__ bool lean_pass_pois(const double *const (&cp)[MAXK], const double *beta_sm, const double *xty,
@@ -738,7 +807,7 @@ __device__ __forceinline__ bool lean_pass_pois(const double *const (&cp)[MAXK], 
         }
         return hi_word(eta);
     };
-    lean_stream<KD>(cp, n, tile, tk, row);
+    lean_rows<KD>(cp, n, tile, tk, row);
     if (__any_sync(0xffffffffu, (tk.smax >= 0x4085E000) | (tk.umax >= 0xC085E000u))) return false; // |eta| >= 700, NaN
 #pragma unroll
     for (int j = 0; j < NH; j++) H[j] = warp_sum(H[j]);
@@ -820,7 +889,7 @@ __device__ __forceinline__ bool lean_pass_bin(const double *const (&cp)[MAXK], c
         }
         return hi_word(eta);
     };
-    lean_stream<KD>(cp, n, tile, tk, row);
+    lean_rows<KD>(cp, n, tile, tk, row);
     const int out_of_range = MLE_ ? ((tk.smax >= 0x40280000) | (tk.umax >= 0xC0762E42u))
                                   : ((tk.smax >= 0x4085E000) | (tk.umax >= 0xC085E000u));
     if (__any_sync(0xffffffffu, out_of_range)) return false;

@@ -24,6 +24,11 @@ struct DataMeta {
     const int *node_gw;       // [n_nodes] ordinal of a Poisson node among the Poisson nodes, -1 otherwise
     int n_pois;               // Poisson nodes: each owns one virtual Gram column, log(y + 0.1) (plan.cuh gram_logy)
     const int *pois_node;     // [n_pois] node of ordinal o (inverse of node_gw)
+    // discrete columns (fit_cell.cuh): byte codes, column-major with ldq bytes per column (16-byte aligned), and
+    // per column max code + 1 if every value is an integer in 0..255, else 0. Null on host builds / when disabled.
+    const unsigned char *Xq;
+    long long ldq;
+    const int *col_card;
 };
 
 struct ResultPtrs {

@@ -1,0 +1,101 @@
+"""BASELINE.json configs at FULL size through the C ABI, each checked against the oracle on a seeded sample
+(configs[0] and configs[1] run at full size with every row checked in test_gpu_parity.py):
+
+  configs[2]  50 binomial nodes x 100 000 rows, mle, max.parents = 4: all 11 576 300 fits
+  configs[3]  100 mixed nodes x 1 000 000 rows, max.parents = 3, mle AND bayes: a 1 048 576-row slice of the
+              16 180 000-row cache (2 048 evenly spaced blocks of 512 consecutive cache rows)
+
+Size-independent properties checked on everything that was scored: every fit returns a flag and a finite
+score (the generator has no separation), aic / bic / mdl are the stated functions of mlik, mlik is monotone
+in nested parent sets for Gaussian children (adding a parent cannot lower the maximised likelihood).
+"""
+import numpy as np
+import pytest
+
+from abn_b200 import _capi as capi
+from abn_b200 import cache as abncache
+from abn_b200 import prep, synth
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-8
+SAMPLE = 1500
+
+
+def _oracle_sample(P, ch0, par, ctrl, res, seed, keys):
+    rng = np.random.default_rng(seed)
+    rows = np.sort(rng.choice(len(ch0), size=SAMPLE, replace=False))
+    ref = H.oracle_score(P, ch0[rows], par[rows], ctrl)
+    assert np.array_equal(res["status"][rows], ref["status"])
+    worst = 0.0
+    for k in keys:
+        rel = H.rel_err(res[k][rows], ref[k])
+        worst = max(worst, float(rel.max()))
+        assert rel.max() < TOL, (k, float(rel.max()))
+    return worst
+
+
+def test_config3_full_size():
+    names, data, dists, mp, _ = synth.make_config(3)
+    d = len(names)
+    assert d == 50 and mp == 4
+    P = prep.prepare(data, dists, "mle")
+    assert P.X.shape[0] == 100_000
+    zero = np.zeros((d, d), dtype=np.int32)
+    ch0, par = abncache.enumerate_candidates(d, zero, zero, mp)
+    assert len(ch0) == 11_576_300
+    ctrl = H.control("mle", d)
+    with abncache.DeviceData(P) as dev:
+        res = dev.score(ch0, par, ctrl)
+        kernels = {k["name"] for k in dev.timing()["kernels"]}
+    assert "fit_cell_kernel<binomial>" in kernels           # every design is all-discrete: contingency tables
+    assert (res["status"] == 0).all() and np.isfinite(res["mlik"]).all()
+    k_par = (par >= 0).sum(axis=1)
+    n = P.X.shape[0]
+    assert np.allclose(res["aic"], -2 * res["mlik"] + 2 * (k_par + 1), rtol=1e-13)
+    assert np.allclose(res["bic"], -2 * res["mlik"] + np.log(n) * (k_par + 1), rtol=1e-13)
+    assert np.allclose(res["mdl"], res["bic"] + (1 + k_par) * np.log(d), rtol=1e-13)
+    _oracle_sample(P, ch0, par, ctrl, res, 20261022, ("mlik", "aic", "bic", "mdl"))
+
+
+@pytest.fixture(scope="module")
+def config4():
+    names, data, dists, mp, _ = synth.make_config(4)
+    d = len(names)
+    zero = np.zeros((d, d), dtype=np.int32)
+    ch0, par = abncache.enumerate_candidates(d, zero, zero, mp)
+    assert len(ch0) == 16_180_000
+    nblk, blk = 2048, 512
+    starts = np.arange(nblk, dtype=np.int64) * (len(ch0) // nblk)
+    sel = (starts[:, None] + np.arange(blk, dtype=np.int64)[None, :]).ravel()
+    return names, data, dists, ch0[sel], par[sel]
+
+
+@pytest.mark.parametrize("method", ["mle", "bayes"])
+def test_config4_one_million_row_slice(config4, method):
+    names, data, dists, ch0, par = config4
+    d = len(names)
+    P = prep.prepare(data, dists, method)
+    assert P.X.shape == (1_000_000, 100) and len(ch0) == 1_048_576
+    ctrl = H.control(method, d)
+    with abncache.DeviceData(P) as dev:
+        res = dev.score(ch0, par, ctrl)
+    assert (res["status"] == 0).all() and np.isfinite(res["mlik"]).all()
+    fam = P.node_family[ch0]
+    if method == "mle":
+        k_par = (par >= 0).sum(axis=1)
+        df = k_par + 1 + (fam == capi.GAUSSIAN)             # Gaussian children count the variance (irls_gaussian_fast.cpp:41)
+        assert np.allclose(res["aic"], -2 * res["mlik"] + 2 * df, rtol=1e-13)
+        assert np.allclose(res["mdl"], res["bic"] + (1 + k_par) * np.log(d), rtol=1e-13)
+        # nested parent sets inside a block of consecutive rows: (child; p1, p2) precedes (child; p1, p2, p3)
+        g = np.flatnonzero(fam == capi.GAUSSIAN)
+        key = {(int(ch0[i]), tuple(par[i][par[i] >= 0])): res["mlik"][i] for i in g[:200_000]}
+        checked = 0
+        for (c, ps), v in key.items():
+            if len(ps) == 3 and (c, ps[:2]) in key:
+                assert v >= key[(c, ps[:2])] - 1e-9 * abs(v)
+                checked += 1
+        assert checked > 50
+    _oracle_sample(P, ch0, par, ctrl, res, 20261023 + (method == "bayes"), ("mlik", "aic", "bic", "mdl") if method == "mle" else ("mlik",))

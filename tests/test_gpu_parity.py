@@ -63,9 +63,18 @@ def test_ex1_vs_oracle(method):
         assert (ref["status"] == 2).sum() == 8  # the non-finite-weight binomial rows b1 ~ {p1, p2, ...}
 
 
+# Rows of mycache.c2.rds whose value differs from the oracle / golden by more than 1e-8 although the oracle is
+# stable under a reversed summation order: none of them is flagged differently. 1637 is an ill-conditioned
+# Gaussian-parent design the reference itself resolves to ~4e-8 (probe: tests/probe_parity.py).
+C2_VALUE_EXCEPTIONS = {1637}
+
+
 @pytest.mark.parametrize("tag", ["c3", "c4", "c2"])
 def test_secondary_goldens_flags_and_values(tag):
-    """inst/extdata/mycache.c*.rds: values on error.code == 0 rows and the error.code = 1 flags."""
+    """inst/extdata/mycache.c*.rds: EVERY error.code identical to the reference's golden, values on the
+    error.code == 0 rows within 1e-8. Exceptions are listed, not tolerated by a quantile: rows on which the
+    oracle disagrees with itself under a reversed summation order (H.oracle_order_sensitive) and
+    C2_VALUE_EXCEPTIONS."""
     z = H.load_npz(f"{tag}_bayes.npz")
     names, data = H.df_from_npz(z)
     dists = H.dists_from_npz(z)
@@ -73,22 +82,30 @@ def test_secondary_goldens_flags_and_values(tag):
     P = prep.prepare(data, dists, "bayes")
     ch0, par = abncache.enumerate_candidates(d, z["banned"], z["retained"], z["max_par"])
     assert np.array_equal(ch0 + 1, z["children"])
-    res = H.gpu_score(P, ch0, par, H.control("bayes", d))
+    ctrl = H.control("bayes", d)
+    res = H.gpu_score(P, ch0, par, ctrl)
     ec = z["error_code"]
-    assert (res["status"] == ec).mean() >= (0.999 if tag == "c2" else 1.0)
+    assert np.array_equal(res["status"], ec)                 # all 56 458 / 294 / 12 flags
+    chaotic, ref, _ = H.oracle_order_sensitive(P, ch0, par, ctrl)
+    assert np.array_equal(ref["status"], ec)
     ok = ec == 0
     rel = H.rel_err(res["mlik"], z["mlik"])
-    if tag == "c2":  # singular designs: a handful of rows are ill-conditioned to 1e-5 in the reference itself
-        assert (rel[ok] > 1e-8).sum() <= 40 and rel[ok].max() < 1e-4
+    rel_o = H.rel_err(res["mlik"], ref["mlik"])
+    stable = ok & ~chaotic
+    over = set(np.flatnonzero(stable & ((rel > TOL) | (rel_o > TOL))).tolist())
+    if tag == "c2":
+        assert over <= C2_VALUE_EXCEPTIONS, sorted(over)
+        assert chaotic.sum() < 500 and rel[ok].max() < 1e-4   # singular designs: min mlik -1.95e24 in the golden
     else:
+        assert not over and chaotic.sum() == 0
         assert rel[ok].max() < 1e-9
-    if tag == "c3":  # the reference's non-modes on its flagged rows are reproduced, not just flagged
-        # (one of the 7, p1 ~ g2, is chaotic in the last bit of the data pass: see tests/test_host_sim.py)
+    if tag == "c3":  # the reference's non-modes on its 7 flagged rows are reproduced, not just flagged
         assert (ec == 1).sum() == 7 and (rel[~ok] < 1e-9).sum() >= 6
 
 
 def test_var33_bayes_vs_oracle():
-    """BASELINE.json configs[1]: var33, method bayes, max.parents = 3 (181 137 fits)."""
+    """BASELINE.json configs[1] at full size: var33, method bayes, max.parents = 3 (181 137 fits): every flag
+    identical to the oracle's, every value within 1e-8 (measured: 8e-15)."""
     z = H.load_npz("var33.npz")
     names, data = H.df_from_npz(z)
     dists = {nm: ("binomial" if isinstance(v, tuple) else "gaussian") for nm, v in data.items()}
@@ -99,12 +116,68 @@ def test_var33_bayes_vs_oracle():
     ctrl = H.control("bayes", d)
     res = H.gpu_score(P, ch0, par, ctrl)
     ref = H.oracle_score(P, ch0, par, ctrl)
-    agree = res["status"] == ref["status"]
-    assert agree.mean() > 0.9995
-    ok = agree & (ref["status"] == 0)
-    rel = H.rel_err(res["mlik"], ref["mlik"])
-    assert np.quantile(rel[ok], 0.999) < TOL
-    assert np.abs(res["mlik"][ok] - ref["mlik"][ok]).mean() / np.abs(ref["mlik"][ok]).mean() < 1e-10
+    assert np.array_equal(res["status"], ref["status"])
+    assert H.rel_err(res["mlik"], ref["mlik"]).max() < TOL
+
+
+def test_near_separation_fuzz_case():
+    """The round-1 fuzz case (small n, strong effects; binomial fits near separation that run to the iteration
+    cap): flags identical and values within 1e-8 on every row whose reference result does not depend on the
+    summation order of its BLAS; the others are counted (tests/test_host_sim.py has the CPU twin)."""
+    from oracle import pyoracle
+    rng = np.random.default_rng(7)
+    fams = ["binomial", "poisson", "gaussian", "binomial", "poisson", "gaussian"]
+    n_chaotic = compared = 0
+    for n, scale in [(40, 2.5), (80, 1.0), (150, 2.5), (400, 0.3), (1500, 1.0), (6000, 2.5)]:
+        zz = rng.standard_normal((n, 3))
+        data, dists = {}, {}
+        for j, f in enumerate(fams):
+            s = rng.uniform(-1, 1) + zz @ rng.normal(0, scale, 3)
+            if f == "binomial":
+                data[f"v{j}"] = (rng.random(n) < 1 / (1 + np.exp(-s))).astype(float)
+            elif f == "poisson":
+                data[f"v{j}"] = rng.poisson(np.exp(np.clip(0.5 + 0.5 * s, -5, 5))).astype(float)
+            else:
+                data[f"v{j}"] = s + rng.standard_normal(n)
+            dists[f"v{j}"] = f
+        if any(np.unique(v).size < 2 for v in data.values()):
+            continue
+        d = len(fams)
+        P = prep.prepare(data, dists, "mle")
+        ch, nd = pyoracle.enumerate_mle(d, np.zeros((d, d), int), np.zeros((d, d), int), 3)
+        ch = ch.astype(np.int32)
+        par = H.parents_from_node_defn(nd, 3)
+        ctrl = H.control("mle", d)
+        res = H.gpu_score(P, ch, par, ctrl)
+        chaotic, ref, _ = H.oracle_order_sensitive(P, ch, par, ctrl)
+        n_chaotic += int(chaotic.sum())
+        assert np.array_equal(res["status"][~chaotic], ref["status"][~chaotic])
+        ok = ~chaotic & (ref["status"] != 2)
+        for k in ("mlik", "aic", "bic", "mdl"):
+            assert H.rel_err(res[k][ok], ref[k][ok]).max() < TOL, (n, k)
+        compared += int(ok.sum())
+    assert compared > 800 and 0 < n_chaotic < 20
+
+
+def test_cells_on_and_off_agree(monkeypatch):
+    """All-discrete designs run on contingency tables (fit_cell.cuh); ABN_B200_NO_CELLS=1 sends them through
+    the streaming kernels instead. Same flags, same scores to 1e-10 (different summation, same fixed point)."""
+    names, data, dists, mp, _ = synth.make_config(4, n=30000, n_nodes=12)
+    d = len(names)
+    for method in ("mle", "bayes"):
+        P = prep.prepare(data, dists, method)
+        ch0, par = abncache.enumerate_candidates(d, np.zeros((d, d), int), np.zeros((d, d), int), 3)
+        ctrl = H.control(method, d)
+        on = H.gpu_score(P, ch0, par, ctrl)
+        monkeypatch.setenv("ABN_B200_NO_CELLS", "1")
+        off = H.gpu_score(P, ch0, par, ctrl)
+        monkeypatch.delenv("ABN_B200_NO_CELLS")
+        assert np.array_equal(on["status"], off["status"])
+        assert H.rel_err(on["mlik"], off["mlik"]).max() < 1e-10
+        fam = P.node_family
+        discrete = np.array([fam[c] != capi.GAUSSIAN and all(p < 0 or fam[p] != capi.GAUSSIAN for p in ps)
+                             for c, ps in zip(ch0, par)])
+        assert discrete.sum() > 100 and not np.array_equal(on["mlik"][discrete], off["mlik"][discrete])  # the path was taken
 
 
 @pytest.mark.parametrize("cfg,method", [(3, "mle"), (4, "mle"), (4, "bayes")])
@@ -359,16 +432,104 @@ def test_wide_designs_generic_kernel(method):
         assert H.rel_err(res[k], ref[k]).max() < TOL, k
 
 
-def test_four_family_fixture_full_cache_runs():
-    """tests/testthat/test-build_score_cache_mle.R:300-324 (expect_no_error): 8 nodes of all four
-    families incl. two 3-level multinomial nodes, max.parents = 7 -> designs up to 12 columns, rank-
-    deficient one-hot blocks, multinomial children. Must not crash; every row gets a status."""
+def test_four_family_fixture_every_row_vs_oracle():
+    """tests/testthat/test-build_score_cache_mle.R:300-324 (the reference only expects no error): 8 nodes of all
+    four families incl. two 3-level multinomial nodes, max.parents = 7 -> designs up to 12 columns, rank-
+    deficient one-hot blocks (rank rule of R/build_score_cache_mle.R:282-306, src/rank.cpp:15-22), multinomial
+    children. EVERY row is compared with the oracle's SVD-rank path:
+      * binomial and Gaussian children (512 rows, 2/3 of them rank deficient with leading columns dropped):
+        flags identical, mlik / aic / bic / mdl within 1e-8;
+      * Poisson children: values within 1e-8 on all 256 rows; flags identical wherever the design has full
+        rank. With both multinomial parents the design is rank deficient, the ridge-regularised IRLS step has
+        a 1e8-amplified rounding-noise component in the null space, and whether ||step|| < 1e-8 is reached
+        within 100 iterations is luck in the reference too (the oracle needs 66 iterations on row 794 and 27
+        with its sums reversed): there only status in {0, 1} is required;
+      * multinomial children: identical where the design fits the 8-column kernel limit; the 2 rows with 7
+        parents (9+ columns) are refused with status 2 (documented limit)."""
     z = H.load_npz("four_family_250.npz")
     names, data = H.df_from_npz(z)
     dists = H.dists_from_npz(z)
+    d = len(names)
     cache = abncache.buildScoreCache(data, dists, method="mle", max_parents=7)
     rows = 8 * 2 ** 7
     assert len(cache["mlik"]) == rows and cache["node.defn"].shape == (rows, 8)
-    assert set(np.unique(cache.status)) <= {0, 1, 2}
-    assert (cache.status == 0).mean() > 0.5
-    assert np.isfinite(cache["mlik"][cache.status == 0]).all()
+    P = prep.prepare(data, dists, "mle")
+    ch0, par = cache["children"] - 1, cache["parents"]
+    ctrl = H.control("mle", d)
+    ref = H.oracle_score(P, ch0, par, ctrl)
+    fam = P.node_family[ch0]
+    multi = [i for i in range(d) if P.node_family[i] == capi.MULTINOMIAL]
+    both_multi = np.array([all(m in ps for m in multi) for ps in par])
+    st, rs = cache.status, ref["status"]
+    bg = (fam == capi.BINOMIAL) | (fam == capi.GAUSSIAN)
+    assert np.array_equal(st[bg], rs[bg])
+    pois = fam == capi.POISSON
+    assert np.array_equal(st[pois & ~both_multi], rs[pois & ~both_multi])
+    assert set(np.unique(st[pois & both_multi])) <= {0, 1}
+    for k in ("mlik", "aic", "bic", "mdl"):
+        assert H.rel_err(cache[k][bg | pois], ref[k][bg | pois]).max() < TOL, k
+    mn = fam == capi.MULTINOMIAL
+    wide = mn & (st == 2) & (rs != 2)
+    assert wide.sum() == 2 and (np.sum(par[wide] >= 0, axis=1) == 7).all()
+    assert np.array_equal(st[mn & ~wide], rs[mn & ~wide])
+    fin = mn & ~wide & (rs != 2)
+    assert H.rel_err(cache["mlik"][fin], ref["mlik"][fin]).max() < 1e-7   # nnet's BFGS: parity unpinned beyond reltol 1e-8
+
+
+def test_rank_deficient_and_near_collinear_designs_vs_oracle():
+    """The rank rule (src/rank.cpp:15-22, R/build_score_cache_mle.R:282-306) on a synthetic set: exactly
+    duplicated columns, an exact linear combination, a constant column and near-collinear columns at relative
+    distances 1e-2 / 1e-3 (full rank for arma::rank and for the Gram-based test alike). Every row against the
+    oracle's SVD rank: same flags, same scores, same mdl (which depends on the number of dropped columns)."""
+    rng = np.random.default_rng(12)
+    n = 4000
+    z = rng.standard_normal((n, 3))
+    b1 = (rng.random(n) < 1 / (1 + np.exp(-z[:, 0]))).astype(float)
+    b2 = (rng.random(n) < 1 / (1 + np.exp(-0.5 * z[:, 1] + 0.3))).astype(float)
+    g1 = z[:, 0] + rng.standard_normal(n)
+    g2 = z[:, 1] - 0.5 * z[:, 2] + rng.standard_normal(n)
+    p1 = rng.poisson(np.exp(0.3 + 0.4 * z[:, 2])).astype(float)
+    data = {"b1": b1, "b2": b2, "b1dup": b1.copy(), "bnot": 1.0 - b1, "g1": g1, "g2": g2, "gsum": g1 + g2,
+            "gnear2": g1 + 1e-2 * rng.standard_normal(n), "gnear3": g2 + 1e-3 * rng.standard_normal(n),
+            "p1": p1, "y": (rng.random(n) < 1 / (1 + np.exp(-0.8 * z[:, 0] + 0.4 * z[:, 1]))).astype(float),
+            "gy": 0.7 * z[:, 0] - 0.2 * z[:, 2] + rng.standard_normal(n)}
+    dists = {k: ("binomial" if k.startswith("b") or k == "y" else "poisson" if k == "p1" else "gaussian") for k in data}
+    names = list(data)
+    d = len(names)
+    P = prep.prepare(data, dists, "mle", centre=False)
+    kids = [names.index(k) for k in ("y", "b2", "p1", "gy")]
+    ch, par = [], []
+    for child in kids:
+        others = [i for i in range(d) if i != child]
+        for size in (2, 3, 4):
+            for _ in range(40):
+                ps = sorted(rng.choice(others, size=size, replace=False).tolist())
+                ch.append(child)
+                par.append(ps + [-1] * (4 - size))
+    ch, par = np.array(ch, np.int32), np.array(par, np.int32)
+    ctrl = H.control("mle", d)
+    res = H.gpu_score(P, ch, par, ctrl)
+    chaotic, ref, _ = H.oracle_order_sensitive(P, ch, par, ctrl)
+    fam = P.node_family[ch]
+    X = np.asarray(P.X)
+    designs = [np.column_stack([np.ones(n)] + [X[:, P.node_col0[p]] for p in ps if p >= 0]) for ps in par]
+    deficient = np.array([np.linalg.matrix_rank(D) < D.shape[1] for D in designs])
+    assert deficient.sum() > 60 and (~deficient).sum() > 60
+    # Where is the reference's convergence FLAG defined? Its stop rule is ||x_new - x||_2 < 1e-8 on coefficients
+    # recomputed from scratch every iteration (solve(X'WX, X'Wz)), so the rounding noise of a solve,
+    # ~ cond(X'X) * 1e-15 * ||x||, sits in that difference. With the 1e-3 near-collinear pair (g2, gnear3)
+    # cond(X'X) is ~1e7 and ||x|| ~ 25..70: noise 5e-8..1.5e-7 against tol 1e-8 - the oracle then converges
+    # after 14..59 iterations on some of these rows and runs to the cap on others, with scores equal to 1e-15
+    # either way (5 of them keep their flag under a reversed summation order, so the order test alone does not
+    # find them all). Flags are therefore compared on every row without that pair and with cond(X'X) < 1e5 (the
+    # triple g1, gsum, gnear3 is the same near-collinearity in disguise) - which includes the 1e-2 pair (cond 2e4) and all exactly deficient binomial designs, where the rank rule drops columns
+    # deterministically; values are compared everywhere.
+    pair3 = np.array([names.index("g2") in ps and names.index("gnear3") in ps for ps in par])
+    cond = np.array([np.inf if df else np.linalg.cond(D) ** 2 for D, df in zip(designs, deficient)])
+    noise_driven = chaotic | pair3 | (~deficient & (cond > 1e5)) | (deficient & (fam != capi.BINOMIAL))
+    strict = ~noise_driven
+    assert strict.sum() > 300 and (strict & deficient).sum() > 30
+    assert np.array_equal(res["status"][strict], ref["status"][strict])
+    cmp_rows = (ref["status"] != 2) & (res["status"] != 2)
+    for k in ("mlik", "aic", "bic", "mdl"):
+        assert H.rel_err(res[k][cmp_rows], ref[k][cmp_rows]).max() < TOL, k
