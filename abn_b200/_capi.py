@@ -18,6 +18,7 @@ BINOMIAL, GAUSSIAN, POISSON, MULTINOMIAL = 1, 2, 3, 4
 METHOD_MLE, METHOD_BAYES = 0, 1
 SOLVER_NEWTON, SOLVER_HYBRID = 0, 1
 FLAG_EXACT_PATH = 1  # abn_control.flags: follow the reference's IRLS pass for pass (include/abn_b200.h)
+FLAG_RESULT_ON_DEVICE = 4  # abn_b200_score: the result pointers are device pointers (include/abn_b200.h)
 FLAG_NO_BIAS_REDUCTION = 2  # binomial mle without the bias reduction (irls_binomial_cpp_fast, fitAbn's first choice)
 FIT_OK, FIT_NOT_CONVERGED, FIT_NON_FINITE = 0, 1, 2
 MAX_K = 32   # widest design
@@ -64,6 +65,9 @@ class Control(C.Structure):
         ("device", C.c_int32),
         ("nvars", C.c_int32),
         ("flags", C.c_int32),
+        ("ngpus", C.c_int32),
+        ("block", C.c_int32),
+        ("devices", C.c_int32 * 16),
     ]
 
 
@@ -97,6 +101,7 @@ class Timing(C.Structure):
         ("kernel_fits", C.c_int64 * MAX_KERNELS),
         ("kernel_bytes", C.c_int64 * MAX_KERNELS),
         ("kernel_ms", C.c_double * MAX_KERNELS),
+        ("kernel_fp64", C.c_int64 * MAX_KERNELS),
     ]
 
 

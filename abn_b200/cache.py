@@ -48,7 +48,10 @@ _DEFAULTS = {
     "seed": 9062019,
 }
 # extra, B200-specific knobs carried in the same control list
-_EXTRA_DEFAULTS = {"solver": "hybrid", "device": 0, "exact.path": False, "bias.reduction": True}
+# ngpus / devices: the analogue of ncores / cluster.type (R/build_score_cache.R:111-112) - the candidate list is split
+# block-cyclically over that many GPUs inside abn_b200_score_cache (one host thread per device)
+_EXTRA_DEFAULTS = {"solver": "hybrid", "device": 0, "exact.path": False, "bias.reduction": True, "ngpus": 1,
+                   "devices": None, "block": 1024}
 
 
 def build_control(method: str = "bayes", **kwargs) -> dict:
@@ -99,7 +102,30 @@ def _flags(ctrl: dict) -> int:
             | (0 if ctrl.get("bias.reduction", True) else capi.FLAG_NO_BIAS_REDUCTION))
 
 
+def _multi_gpu(c: capi.Control, ctrl: dict) -> capi.Control:
+    ngpus = int(ctrl.get("ngpus", 1) or 1)
+    devices = ctrl.get("devices")
+    if devices is not None:
+        devices = [int(x) for x in devices]
+        ngpus = len(devices)
+    else:
+        devices = list(range(ngpus))
+    if ngpus > 16:
+        raise ValueError("`ngpus` must be at most 16")
+    c.ngpus = ngpus if ngpus > 1 else 0
+    c.block = int(ctrl.get("block", 1024) or 1024)
+    for i in range(16):
+        c.devices[i] = devices[i] if i < len(devices) else i
+    if ngpus == 1 and ctrl.get("devices") is not None:
+        c.device = devices[0]
+    return c
+
+
 def to_c_control(ctrl: dict, method: str, nvars: int) -> capi.Control:
+    return _multi_gpu(_to_c_control(ctrl, method, nvars), ctrl)
+
+
+def _to_c_control(ctrl: dict, method: str, nvars: int) -> capi.Control:
     solver = ctrl.get("solver", "hybrid")
     solver_code = {"hybrid": capi.SOLVER_HYBRID, "newton": capi.SOLVER_NEWTON}.get(solver, solver)
     if method == "bayes":
@@ -223,13 +249,26 @@ def kernel_name(kid: int) -> str:
         return "gauss_kernel"
     cell0 = 2 + 6 * (capi.FAST_K + 1) * 2  # plan.cuh CELL_BUCKET0
     if kid >= cell0:
-        return f"fit_cell_kernel<{('binomial', 'poisson')[kid - cell0]}>"
+        return f"fit_cell_kernel<{('binomial', 'poisson')[(kid - cell0) >> 1]},{('small', 'large')[(kid - cell0) & 1]}>"
     code = kid - 2
     icpt, fk = code & 1, code >> 1
     fam, k = divmod(fk, capi.FAST_K + 1)
     if fam >= 2:
         return f"fit_mn_kernel<L={fam},K={k},icpt={icpt}>"
     return f"fit_kernel<{('binomial', 'poisson')[fam]},K={k},icpt={icpt}>"
+
+
+def score_cache_one_shot(prepared: _prep.Prepared, children0, parents, control: capi.Control) -> dict:
+    """``abn_b200_score_cache``: upload, Gram, fits and download in one call with host buffers; with
+    ``control.ngpus > 1`` on that many devices (include/abn_b200.h)."""
+    L = capi.lib()
+    ds, k1 = capi.make_dataset(prepared.X, prepared.node_family, prepared.node_col0)
+    cd, k2 = capi.make_candidates(children0, parents)
+    res, arrs = capi.make_result(cd.rows, control.method)
+    err = C.create_string_buffer(512)
+    capi.check(L.abn_b200_score_cache(C.byref(ds), C.byref(cd), C.byref(control), C.byref(res), err, len(err)), err)
+    del k1, k2
+    return arrs
 
 
 class DeviceData:
@@ -255,12 +294,38 @@ class DeviceData:
         del keep
         return arrs
 
+    def score_to_slab(self, children0, parents, control: capi.Control, slab) -> None:
+        """Scores into a device-resident result slab (abn_b200/shard.py: torch float64 (5, L) on this handle's
+        device) with ABN_FLAG_RESULT_ON_DEVICE: the kernels write mlik / aic / bic / mdl / status / iters there
+        and nothing comes back to the host - the slab goes straight into the rank's all_gather."""
+        import torch
+        L = capi.lib()
+        cd, keep = capi.make_candidates(children0, parents)
+        n, Ls = cd.rows, slab.shape[1]
+        assert slab.is_cuda and slab.dtype == torch.float64 and slab.is_contiguous() and slab.shape[0] == 5 and n <= Ls
+        base = slab.data_ptr()
+        res = capi.Result()
+        res.mlik = C.cast(base, capi.c_double_p)
+        if control.method == capi.METHOD_MLE:
+            res.aic = C.cast(base + 8 * Ls, capi.c_double_p)
+            res.bic = C.cast(base + 16 * Ls, capi.c_double_p)
+            res.mdl = C.cast(base + 24 * Ls, capi.c_double_p)
+        res.status = C.cast(base + 32 * Ls, capi.c_int32_p)
+        res.iters = C.cast(base + 36 * Ls, capi.c_int32_p)
+        ctrl = capi.Control.from_buffer_copy(control)
+        ctrl.flags |= capi.FLAG_RESULT_ON_DEVICE
+        err = C.create_string_buffer(512)
+        torch.cuda.current_stream(slab.device).synchronize()  # the library writes on its own stream
+        capi.check(L.abn_b200_score(self._h, C.byref(cd), C.byref(ctrl), C.byref(res), err, len(err)), err)
+        del keep
+
     def timing(self) -> dict:
         t = capi.Timing()
         capi.lib().abn_b200_last_timing(self._h, C.byref(t))
         out = {k: getattr(t, k) for k in ("h2d_ms", "plan_ms", "fit_ms", "d2h_ms", "launches", "algo_bytes")}
         out["kernels"] = [{"id": t.kernel_id[i], "name": kernel_name(t.kernel_id[i]), "fits": t.kernel_fits[i],
-                           "bytes": t.kernel_bytes[i], "ms": t.kernel_ms[i]} for i in range(t.n_kernels)]
+                           "bytes": t.kernel_bytes[i], "ms": t.kernel_ms[i], "fp64": t.kernel_fp64[i]}
+                          for i in range(t.n_kernels)]
         return out
 
     def close(self):
@@ -390,9 +455,14 @@ def buildScoreCache(data_df=None, data_dists=None, method="bayes", group_var=Non
         return out
 
     cctrl = to_c_control(ctrl, method, d)
-    with DeviceData(P, device=int(ctrl.get("device", 0))) as dev:
-        res = dev.score(children0, parents, cctrl)
-        out.timing = dev.timing()
+    if cctrl.ngpus > 1:
+        # control = {"ngpus": N} / {"devices": [...]}: the one-shot C-ABI call splits the list over the devices
+        res = score_cache_one_shot(P, children0, parents, cctrl)
+        out.timing = None
+    else:
+        with DeviceData(P, device=int(cctrl.device)) as dev:
+            res = dev.score(children0, parents, cctrl)
+            out.timing = dev.timing()
     out.passes = res["iters"]
     out.status = res["status"]
 

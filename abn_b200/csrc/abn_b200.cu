@@ -2,16 +2,15 @@
 // Gram-only Gaussian kernels and the dispatch of the streaming fit kernels.
 #include <cuda_runtime.h>
 
-#include <chrono>
-#include <cstdio>
-#include <cstdlib>
-
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -29,9 +28,33 @@ cudaError_t abn_wide_launch(const abnc::DataMeta &m, const abnc::Control &c, con
                             cudaStream_t stream);
 int abn_wide_max_k();
 // fit_cell.cu: all-discrete designs on contingency tables (kind: RK_BIN_MLE, RK_POIS, RK_BIN_BAYES)
-cudaError_t abn_cell_launch(int kind, const abnc::DataMeta &m, const abnc::Control &c, const abn::FitDesc *descs,
+cudaError_t abn_cell_launch(int kind, int large, const abnc::DataMeta &m, const abnc::Control &c, const abn::FitDesc *descs,
                             const int *child, const int *list, int count, int *counter, abnc::ResultPtrs out,
                             int sm_count, cudaStream_t stream);
+
+// per-bucket slot of abn_data::dCounters: [0] work-queue head, [2..15] 64-bit pass tallies by PassMode (fit_kernel.cuh)
+constexpr int BUCKET_SLOT_INTS = 16;
+
+// FP64 instructions one observation row costs in a pass of the streaming kernels, by row kind, design width and pass
+// mode - counted from the SASS of the lean passes (profiles/sass_r2_*; e.g. Poisson K = 4: 3 eta + 10 exp + 13 H = 26,
+// binomial K = 4 HG: 3 + 10 + 1 + 3 rcp + 1 w + 13 H + 4 S = 35). The rare careful / no-intercept passes are
+// counted with the same formula.
+static int fp64_per_row(int fam /*0 binomial, 1 Poisson*/, int k, int mode)
+{
+    const bool need_h = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_HESS || mode == PASS_PINIT);
+    const bool need_g = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_GRAD || mode == PASS_PINIT);
+    const bool need_l = (mode == PASS_FULL || mode == PASS_LL);
+    const int kd = k > 0 ? k - 1 : 0;
+    const int hsum = 1 + 2 * kd + k * kd / 2; // w; w x_q; (w x_p); (w x_p) x_q
+    int c = kd + 10;                          // eta, exp (fast_exp64r)
+    if (fam == 1) return c + (need_h ? hsum : (need_g ? 1 + kd : 1));
+    c += 1;                                   // d = 1 + e
+    if (need_l) c += 13;                      // log(1 + e) and its sum
+    if (need_h || need_g) c += 3;             // reciprocal
+    if (need_h) c += 1 + hsum;
+    if (need_g) c += 1 + kd;
+    return c;
+}
 
 static_assert(ABN_FAST_K == MAXK, "include/abn_b200.h and solver.cuh disagree on the fast-path design width");
 static_assert(MN_MAXL == MN_MAXL_, "plan.cuh and solver_mn.cuh disagree on the multinomial level limit");
@@ -288,7 +311,8 @@ __global__ void resolve_kernel(const DataMeta m, int method, int flags, long lon
     if (d.k == 0 || (d.family == MULTINOMIAL && (d.nlev < 2 || d.nlev > MN_MAXL || method != MLE))) d.err = d.err ? d.err : 2;
     descs[r] = d;
     int key = bucket_of(d);
-    if (cell_eligible(m, d, method, flags)) key = CELL_BUCKET0 + (d.family == POISSON ? 1 : 0);
+    const int cell = cell_eligible(m, d, method, flags);
+    if (cell) key = CELL_BUCKET0 + (d.family == POISSON ? 2 : 0) + (cell - 1);
     keys[r] = (unsigned char)key;
     idx[r] = (int)r;
 }
@@ -517,7 +541,7 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     TRY_OR_FREE(dev_alloc(&d->dGwIndex, (size_t)ds->n_nodes * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dPoisNode, std::max<size_t>(1, pois_node.size()) * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dBucketStart, (size_t)(NBUCKETS_ALL + 1) * sizeof(int), d->stream));
-    TRY_OR_FREE(dev_alloc(&d->dCounters, (size_t)(NBUCKETS_ALL + 1) * sizeof(int), d->stream));
+    TRY_OR_FREE(dev_alloc(&d->dCounters, (size_t)(NBUCKETS_ALL + 1) * BUCKET_SLOT_INTS * sizeof(int), d->stream));
     // ABN_B200_NO_CELLS=1: every fit takes the streaming kernels (A/B runs, debugging)
     const char *no_cells = std::getenv("ABN_B200_NO_CELLS");
     const bool use_cells = !(no_cells && *no_cells && *no_cells != '0');
@@ -602,6 +626,77 @@ static int ensure_scratch(abn_data *d, long long rows, int width, char *err, siz
     return ABN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-call bookkeeping on the device: candidate validation and the roofline account (no host sweeps)
+// ---------------------------------------------------------------------------------------------
+// first invalid row (child out of range, parent out of range / below -1 / equal to the child), or INT_MAX
+__global__ void validate_kernel(long long rows, int width, int n_nodes, const int *__restrict__ child,
+                                const int *__restrict__ parents, int *__restrict__ first_bad)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int c = child[r];
+    bool bad = c < 0 || c >= n_nodes;
+    for (int j = 0; j < width; j++) {
+        const int p = parents[r * width + j];
+        bad |= p < -1 || p >= n_nodes || p == c;
+    }
+    if (bad) atomicMin(first_bad, (int)r);
+}
+
+// per bucket: sum over its fits of passes x (k_data + response columns) - times n x 8 that is SURVEY 8d's
+// algorithmic bytes - and, for the contingency-table buckets, of the byte columns read once
+__global__ void __launch_bounds__(256)
+account_kernel(long long rows, const unsigned char *__restrict__ keys_sorted, const int *__restrict__ idx_sorted,
+               const FitDesc *__restrict__ descs, const int *__restrict__ iters, unsigned long long *__restrict__ units)
+{
+    __shared__ unsigned long long acc[NBUCKETS_ALL];
+    for (int i = threadIdx.x; i < NBUCKETS_ALL; i += blockDim.x) acc[i] = 0ull;
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < rows) {
+        const int key = keys_sorted[t], row = idx_sorted[t];
+        const FitDesc d = descs[row];
+        unsigned long long u;
+        if (key >= CELL_BUCKET0) u = (unsigned long long)(d.kdata + (d.family == BINOMIAL ? 1 : 0));
+        else u = (unsigned long long)iters[row] * (unsigned long long)(d.kdata + d.nlev);
+        atomicAdd(&acc[key], u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NBUCKETS_ALL; i += blockDim.x)
+        if (acc[i]) atomicAdd(&units[i], acc[i]);
+}
+
+// Everything one abn_b200_score call creates; released on every exit path. The destructor first drains the
+// main and the side streams, so no kernel is still writing into a buffer that is being freed.
+struct ScoreCall {
+    abn_data *d;
+    std::vector<cudaEvent_t> events;
+    std::vector<void *> buffers;
+    explicit ScoreCall(abn_data *dd) : d(dd) {}
+    cudaError_t event(cudaEvent_t *e, unsigned flags = cudaEventDefault)
+    {
+        cudaError_t rc = cudaEventCreateWithFlags(e, flags);
+        if (rc == cudaSuccess) events.push_back(*e);
+        return rc;
+    }
+    template <typename T>
+    cudaError_t alloc(T **p, size_t bytes)
+    {
+        cudaError_t rc = dev_alloc(p, bytes, d->stream);
+        if (rc == cudaSuccess) buffers.push_back(*p);
+        return rc;
+    }
+    ~ScoreCall()
+    {
+        for (auto &ss : d->side) if (ss) cudaStreamSynchronize(ss);
+        for (void *p : buffers) dev_free(p, d->stream);
+        cudaStreamSynchronize(d->stream);
+        for (auto &e : events) cudaEventDestroy(e);
+        cudaGetLastError();
+    }
+};
+
 extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn_control *ctrl, abn_result *out,
                               char *err, size_t errlen)
 {
@@ -613,28 +708,28 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
         for (int f : d->family)
             if (f == ABN_MULTINOMIAL)
                 return fail(err, errlen, ABN_ERR_ARG, "Multinomial nodes are not yet implemented for method 'bayes'. Try with method='mle'.");
+    const bool on_device = (ctrl->flags & ABN_FLAG_RESULT_ON_DEVICE) != 0;
+    const int coef_stride = out->coef ? out->coef_stride : 0;
+    if (out->coef && coef_stride < 1) return fail(err, errlen, ABN_ERR_ARG, "coef_stride must be positive when coef is given");
+    if (out->se && !out->coef) return fail(err, errlen, ABN_ERR_ARG, "se needs coef (they share coef_stride)");
+    if (on_device && (out->coef || out->se || out->sse))
+        return fail(err, errlen, ABN_ERR_ARG, "ABN_FLAG_RESULT_ON_DEVICE covers mlik / aic / bic / mdl / status / iters only");
+    if (on_device && !out->mlik) return fail(err, errlen, ABN_ERR_ARG, "ABN_FLAG_RESULT_ON_DEVICE needs a device pointer for mlik");
     const long long rows = cand->rows;
     const int width = cand->max_parents;
     d->timing = abn_timing{};
     if (rows == 0) return ABN_OK;
     if (!cand->child || (width > 0 && !cand->parents)) return fail(err, errlen, ABN_ERR_ARG, "null candidate arrays");
-    // host-side validation of indices (cheap relative to the upload)
-    for (long long r = 0; r < rows; r++) {
-        if (cand->child[r] < 0 || cand->child[r] >= d->m.n_nodes) return fail(err, errlen, ABN_ERR_ARG, "row %lld: child %d out of range", r, cand->child[r]);
-        for (int j = 0; j < width; j++) {
-            const int p = cand->parents[r * width + j];
-            if (p >= d->m.n_nodes || p == cand->child[r]) return fail(err, errlen, ABN_ERR_ARG, "row %lld: parent %d invalid", r, p);
-        }
-    }
     CUDA_TRY(cudaSetDevice(d->device));
     PhaseTrace tr;
     int rc = ensure_scratch(d, rows, width, err, errlen);
     if (rc != ABN_OK) return rc;
     tr.mark("score: scratch");
 
-    cudaEvent_t ev[5];
-    for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+    ScoreCall call(d);
     cudaStream_t s = d->stream;
+    cudaEvent_t ev[5];
+    for (auto &e : ev) CUDA_TRY(call.event(&e));
     long long launches = 0;
 
     CUDA_TRY(cudaEventRecord(ev[0], s));
@@ -644,40 +739,63 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
 
     Control c{ctrl->method, ctrl->max_iters, ctrl->solver, ctrl->nvars, ctrl->tol, ctrl->epsabs,
               ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale, ctrl->flags};
-    double *dCoef = nullptr;
-    const int coef_stride = out->coef ? out->coef_stride : 0;
+    double *dCoef = nullptr, *dSe = nullptr, *dSse = nullptr;
     if (out->coef) {
-        if (coef_stride < 1) return fail(err, errlen, ABN_ERR_ARG, "coef_stride must be positive when coef is given");
-        CUDA_TRY(dev_alloc(&dCoef, (size_t)rows * coef_stride * sizeof(double), s));
+        CUDA_TRY(call.alloc(&dCoef, (size_t)rows * coef_stride * sizeof(double)));
         CUDA_TRY(cudaMemsetAsync(dCoef, 0xff, (size_t)rows * coef_stride * sizeof(double), s)); // all-ones = NaN
     }
-    double *dSe = nullptr;
     if (out->se) {
-        if (!out->coef) return fail(err, errlen, ABN_ERR_ARG, "se needs coef (they share coef_stride)");
-        CUDA_TRY(dev_alloc(&dSe, (size_t)rows * coef_stride * sizeof(double), s));
+        CUDA_TRY(call.alloc(&dSe, (size_t)rows * coef_stride * sizeof(double)));
         CUDA_TRY(cudaMemsetAsync(dSe, 0xff, (size_t)rows * coef_stride * sizeof(double), s));
     }
-    ResultPtrs rp{d->dRes, d->dRes + d->cap_rows, d->dRes + 2 * d->cap_rows, d->dRes + 3 * d->cap_rows, d->dStatus, d->dIters,
-                  dCoef, coef_stride, dSe, nullptr};
-    double *dSse = nullptr;
     if (out->sse) {
-        CUDA_TRY(dev_alloc(&dSse, (size_t)rows * sizeof(double), s));
+        CUDA_TRY(call.alloc(&dSse, (size_t)rows * sizeof(double)));
         CUDA_TRY(cudaMemsetAsync(dSse, 0xff, (size_t)rows * sizeof(double), s));
-        rp.sse = dSse;
+    }
+    // where the kernels write: the handle's scratch slabs, or straight into the caller's device buffers
+    ResultPtrs rp{d->dRes, d->dRes + d->cap_rows, d->dRes + 2 * d->cap_rows, d->dRes + 3 * d->cap_rows, d->dStatus, d->dIters,
+                  dCoef, coef_stride, dSe, dSse};
+    if (on_device) {
+        rp.mlik = out->mlik; rp.aic = out->aic; rp.bic = out->bic; rp.mdl = out->mdl;
+        rp.status = out->status ? out->status : d->dStatus;
+        rp.iters = out->iters ? out->iters : d->dIters;
     }
 
+    // per-call device words: [0] first invalid row, then per bucket the roofline units (account_kernel)
+    unsigned long long *dAcct = nullptr;
+    CUDA_TRY(call.alloc(&dAcct, (size_t)(1 + NBUCKETS_ALL) * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(dAcct, 0, (size_t)(1 + NBUCKETS_ALL) * sizeof(unsigned long long), s));
+    int *dFirstBad = reinterpret_cast<int *>(dAcct);
+    const int int_max = 2147483647;
+    CUDA_TRY(cudaMemcpyAsync(dFirstBad, &int_max, sizeof(int), cudaMemcpyHostToDevice, s));
+
     const int tb = 128;
+    validate_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(rows, width, d->m.n_nodes, d->dChild, d->dParents, dFirstBad);
+    KCHECK("validate_kernel", s);
+    int first_bad = int_max;
+    CUDA_TRY(cudaMemcpyAsync(&first_bad, dFirstBad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (first_bad != int_max) {
+        const long long r = first_bad;
+        const int ch = cand->child[r];
+        if (ch < 0 || ch >= d->m.n_nodes) return fail(err, errlen, ABN_ERR_ARG, "row %lld: child %d out of range", r, ch);
+        for (int j = 0; j < width; j++) {
+            const int p = cand->parents[r * width + j];
+            if (p < -1 || p >= d->m.n_nodes || p == ch) return fail(err, errlen, ABN_ERR_ARG, "row %lld: parent %d invalid", r, p);
+        }
+        return fail(err, errlen, ABN_ERR_ARG, "row %lld: invalid candidate", r);
+    }
     resolve_kernel<<<(unsigned)((rows + tb - 1) / tb), tb, 0, s>>>(d->m, c.method, c.flags, rows, width, d->dChild, d->dParents,
                                                                   d->dDescs, d->dKeys, d->dIdx);
     KCHECK("resolve_kernel", s);
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(d->dSortTmp, d->sortTmpBytes, d->dKeys, d->dKeysSorted, d->dIdx, d->dIdxSorted,
                                              (int)rows, 0, 8, s));
     CUDA_TRY(cudaMemsetAsync(d->dBucketStart, 0xff, (size_t)(NBUCKETS_ALL + 1) * sizeof(int), s));
-    CUDA_TRY(cudaMemsetAsync(d->dCounters, 0, (size_t)(NBUCKETS_ALL + 1) * sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(d->dCounters, 0, (size_t)(NBUCKETS_ALL + 1) * BUCKET_SLOT_INTS * sizeof(int), s));
     KCHECK("radix sort", s);
     bucket_bounds<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(d->dKeysSorted, rows, d->dBucketStart);
     KCHECK("bucket_bounds", s);
-    launches += 3;
+    launches += 4;
     int hstart[NBUCKETS_ALL + 1];
     CUDA_TRY(cudaMemcpyAsync(hstart, d->dBucketStart, sizeof(hstart), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -692,10 +810,10 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     // the large buckets follow on the main stream in cache order. Per-kernel CUDA events are recorded
     // on the stream the kernel runs on.
     std::vector<cudaEvent_t> kev0, kev1;
-    std::vector<int> kid, kcount, kstart;
+    std::vector<int> kid, kcount;
     const int small_limit = d->sm_count * ABN_MIN_BLOCKS * FIT_WARPS * 2;
     cudaEvent_t planned;
-    CUDA_TRY(cudaEventCreateWithFlags(&planned, cudaEventDisableTiming));
+    CUDA_TRY(call.event(&planned, cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(planned, s));
     for (auto &ss : d->side) CUDA_TRY(cudaStreamWaitEvent(ss, planned, 0));
     int n_side = 0;
@@ -713,21 +831,21 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
             const bool timed = ((int)kid.size() < ABN_MAX_KERNELS);
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (timed) {
-                CUDA_TRY(cudaEventCreate(&e0));
-                CUDA_TRY(cudaEventCreate(&e1));
+                CUDA_TRY(call.event(&e0));
+                CUDA_TRY(call.event(&e1));
                 CUDA_TRY(cudaEventRecord(e0, ks));
             }
             const int *list = d->dIdxSorted + hstart[b];
+            int *slot = d->dCounters + b * BUCKET_SLOT_INTS;
             if (b == 0) {
                 // not for the register-resident kernels: wider than 8 columns (-> generic wide kernel,
                 // which re-resolves the design with its own limit and flags what it cannot take)
-                CUDA_TRY(abn_wide_launch(d->m, c, d->dChild, d->dParents, width, list, count, d->dCounters + b, rp,
-                                         d->sm_count, ks));
+                CUDA_TRY(abn_wide_launch(d->m, c, d->dChild, d->dParents, width, list, count, slot, rp, d->sm_count, ks));
             } else if (b == 1) {
                 gauss_kernel<<<(count + 127) / 128, 128, 0, ks>>>(d->m, c, d->dDescs, d->dChild, list, count, rp);
             } else if (b >= CELL_BUCKET0) {
-                const int kind = (b == CELL_BUCKET0 + 1) ? RK_POIS : (c.method == MLE ? RK_BIN_MLE : RK_BIN_BAYES);
-                CUDA_TRY(abn_cell_launch(kind, d->m, c, d->dDescs, d->dChild, list, count, d->dCounters + b, rp, d->sm_count, ks));
+                const int kind = (b >= CELL_BUCKET0 + 2) ? RK_POIS : (c.method == MLE ? RK_BIN_MLE : RK_BIN_BAYES);
+                CUDA_TRY(abn_cell_launch(kind, (b - CELL_BUCKET0) & 1, d->m, c, d->dDescs, d->dChild, list, count, slot, rp, d->sm_count, ks));
             } else {
                 const int code = b - 2, icpt = code & 1, fk = code >> 1, fam = fk / (MAXK + 1), k = fk % (MAXK + 1);
                 FitLaunchFn fn = nullptr;
@@ -737,13 +855,13 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
                 else mfn = get_launch_mn(fam, k, icpt);
                 if (mfn) {
                     int grid = std::min((count + MN_WARPS - 1) / MN_WARPS, d->sm_count * 2);
-                    CUDA_TRY(mfn(d->m, c, d->dDescs, list, count, d->dCounters + b, rp, grid, ks));
+                    CUDA_TRY(mfn(d->m, c, d->dDescs, list, count, slot, rp, grid, ks));
                 } else if (!fn) {
                     n_unsupported += count;
                     unsupported_kernel<<<(count + 255) / 256, 256, 0, ks>>>(list, count, rp);
                 } else {
                     int grid = std::min((count + FIT_WARPS - 1) / FIT_WARPS, d->sm_count * ABN_MIN_BLOCKS);
-                    CUDA_TRY(fn(d->m, c, d->dDescs, d->dChild, list, count, d->dCounters + b, rp, grid, ks));
+                    CUDA_TRY(fn(d->m, c, d->dDescs, d->dChild, list, count, slot, rp, grid, ks));
                 }
             }
             {
@@ -757,41 +875,40 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
                 kev1.push_back(e1);
                 kid.push_back(b);
                 kcount.push_back(count);
-                kstart.push_back(hstart[b]);
             }
             launches++;
         }
     }
     for (int i = 0; i < std::min(n_side, (int)abn_data::NSIDE); i++) {
         cudaEvent_t done;
-        CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        CUDA_TRY(call.event(&done, cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(done, d->side[i]));
         CUDA_TRY(cudaStreamWaitEvent(s, done, 0));
-        cudaEventDestroy(done); // released once it has completed
     }
-    cudaEventDestroy(planned);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev[3], s));
-    std::vector<int> sorted_rows(rows);
-    CUDA_TRY(cudaMemcpyAsync(sorted_rows.data(), d->dIdxSorted, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (out->mlik) CUDA_TRY(cudaMemcpyAsync(out->mlik, rp.mlik, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (ctrl->method == ABN_METHOD_MLE) {
-        if (out->aic) CUDA_TRY(cudaMemcpyAsync(out->aic, rp.aic, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
-        if (out->bic) CUDA_TRY(cudaMemcpyAsync(out->bic, rp.bic, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
-        if (out->mdl) CUDA_TRY(cudaMemcpyAsync(out->mdl, rp.mdl, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+    // roofline account on the device (a few hundred bytes come back instead of two O(rows) host sweeps)
+    account_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(rows, d->dKeysSorted, d->dIdxSorted, d->dDescs, rp.iters, dAcct + 1);
+    KCHECK("account_kernel", s);
+    launches++;
+    unsigned long long units[NBUCKETS_ALL];
+    std::vector<int> slots((size_t)NBUCKETS_ALL * BUCKET_SLOT_INTS);
+    CUDA_TRY(cudaMemcpyAsync(units, dAcct + 1, sizeof(units), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(slots.data(), d->dCounters, slots.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (!on_device) {
+        if (out->mlik) CUDA_TRY(cudaMemcpyAsync(out->mlik, rp.mlik, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (ctrl->method == ABN_METHOD_MLE) {
+            if (out->aic) CUDA_TRY(cudaMemcpyAsync(out->aic, rp.aic, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+            if (out->bic) CUDA_TRY(cudaMemcpyAsync(out->bic, rp.bic, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+            if (out->mdl) CUDA_TRY(cudaMemcpyAsync(out->mdl, rp.mdl, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        if (out->status) CUDA_TRY(cudaMemcpyAsync(out->status, rp.status, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (out->iters) CUDA_TRY(cudaMemcpyAsync(out->iters, rp.iters, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (dCoef) CUDA_TRY(cudaMemcpyAsync(out->coef, dCoef, (size_t)rows * coef_stride * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (dSe) CUDA_TRY(cudaMemcpyAsync(out->se, dSe, (size_t)rows * coef_stride * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (dSse) CUDA_TRY(cudaMemcpyAsync(out->sse, dSse, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
-    if (out->status) CUDA_TRY(cudaMemcpyAsync(out->status, rp.status, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (dCoef) CUDA_TRY(cudaMemcpyAsync(out->coef, dCoef, (size_t)rows * coef_stride * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (dSe) CUDA_TRY(cudaMemcpyAsync(out->se, dSe, (size_t)rows * coef_stride * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (dSse) CUDA_TRY(cudaMemcpyAsync(out->sse, dSse, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, s));
-    std::vector<int> iters_host;
-    int *iters_dst = out->iters;
-    if (!iters_dst) { iters_host.resize(rows); iters_dst = iters_host.data(); }
-    CUDA_TRY(cudaMemcpyAsync(iters_dst, rp.iters, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaEventRecord(ev[4], s));
-    dev_free(dCoef, s);
-    dev_free(dSe, s);
-    dev_free(dSse, s);
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
     tr.mark("score: upload + plan + fits + download");
@@ -805,50 +922,128 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     d->timing.launches = launches;
     // algorithmic bytes: passes * n * (k_data + 1) * 8 per streamed fit; a fit on a contingency table
     // (fit_cell.cuh) reads its byte-coded columns once: n * (k_data + 1 for a binomial response)
-    auto fit_bytes = [&](long long r, bool cell) {
-        int kd = 0;
-        for (int j = 0; j < width; j++) {
-            const int p = cand->parents[r * width + j];
-            if (p >= 0) kd += d->col0[p + 1] - d->col0[p];
-        }
-        const int ch = cand->child[r];
-        const int yw = d->col0[ch + 1] - d->col0[ch];
-        if (cell) return (long long)d->m.n * (kd + (d->family[ch] == ABN_BINOMIAL ? 1 : 0));
-        return (long long)iters_dst[r] * d->m.n * (kd + yw) * 8;
-    };
     long long bytes = 0;
     d->timing.n_kernels = (int)kid.size();
     for (size_t i = 0; i < kid.size(); i++) {
+        const int b = kid[i];
         float kms = 0;
         cudaEventElapsedTime(&kms, kev0[i], kev1[i]);
-        long long kb = 0;
-        for (int t = 0; t < kcount[i]; t++) kb += fit_bytes(sorted_rows[kstart[i] + t], kid[i] >= CELL_BUCKET0);
+        const long long kb = (long long)units[b] * d->m.n * (b >= CELL_BUCKET0 ? 1 : 8);
         bytes += kb;
-        d->timing.kernel_id[i] = kid[i];
+        long long fp64 = 0;
+        if (b >= 2 && b < CELL_BUCKET0) {
+            const int fk = (b - 2) >> 1, fam = fk / (MAXK + 1), k = fk % (MAXK + 1);
+            if (fam <= 1) {
+                const unsigned long long *tally = reinterpret_cast<const unsigned long long *>(slots.data() + (size_t)b * BUCKET_SLOT_INTS + 2);
+                for (int mode = 1; mode <= 6; mode++) fp64 += (long long)tally[mode] * d->m.n * fp64_per_row(fam, k, mode);
+            }
+        }
+        d->timing.kernel_id[i] = b;
         d->timing.kernel_fits[i] = kcount[i];
         d->timing.kernel_bytes[i] = kb;
         d->timing.kernel_ms[i] = kms;
+        d->timing.kernel_fp64[i] = fp64;
     }
     d->timing.algo_bytes = bytes;
-    for (auto &e : kev0) cudaEventDestroy(e);
-    for (auto &e : kev1) cudaEventDestroy(e);
-    for (auto &e : ev) cudaEventDestroy(e);
     tr.mark("score: timing bookkeeping");
     if (n_unsupported > 0 && n_unsupported == rows)
         return fail(err, errlen, ABN_ERR_LIMIT, "no candidate could be scored by the fast kernels");
     return ABN_OK;
 }
 
-extern "C" int abn_b200_score_cache(const abn_dataset *ds, const abn_candidates *cand, const abn_control *ctrl,
-                                    abn_result *out, char *err, size_t errlen)
+static int score_cache_on(const abn_dataset *ds, const abn_candidates *cand, const abn_control *ctrl, int device,
+                          abn_result *out, char *err, size_t errlen)
 {
-    if (!ctrl) return fail(err, errlen, ABN_ERR_ARG, "null control");
     abn_data *d = nullptr;
-    int rc = abn_b200_data_create(ds, ctrl->device, &d, err, errlen);
+    int rc = abn_b200_data_create(ds, device, &d, err, errlen);
     if (rc != ABN_OK) return rc;
     rc = abn_b200_score(d, cand, ctrl, out, err, errlen);
     abn_b200_data_destroy(d);
     return rc;
+}
+
+// rows device `rank` of `world` owns under the block-cyclic split: blocks rank, rank + world, ...
+static long long shard_rows(long long rows, int block, int world, int rank)
+{
+    const long long nblocks = (rows + block - 1) / block;
+    long long mine = 0;
+    for (long long b = rank; b < nblocks; b += world) mine += std::min<long long>(block, rows - b * block);
+    return mine;
+}
+
+extern "C" int abn_b200_score_cache(const abn_dataset *ds, const abn_candidates *cand, const abn_control *ctrl,
+                                    abn_result *out, char *err, size_t errlen)
+{
+    if (!ctrl || !cand || !out) return fail(err, errlen, ABN_ERR_ARG, "null argument");
+    if (ctrl->flags & ABN_FLAG_RESULT_ON_DEVICE)
+        return fail(err, errlen, ABN_ERR_ARG, "ABN_FLAG_RESULT_ON_DEVICE needs a resident data set (abn_b200_score)");
+    const int world = ctrl->ngpus;
+    if (world <= 1) return score_cache_on(ds, cand, ctrl, world == 1 ? ctrl->devices[0] : ctrl->device, out, err, errlen);
+
+    // ---- one host thread per device; every device holds the data set and scores its blocks of the list ----------
+    if (world > ABN_MAX_DEVICES) return fail(err, errlen, ABN_ERR_ARG, "ngpus = %d exceeds ABN_MAX_DEVICES = %d", world, ABN_MAX_DEVICES);
+    const int ndev = abn_b200_device_count();
+    if (ndev == 0) return fail(err, errlen, ABN_ERR_NO_GPU, "no CUDA device available; this library has no CPU path");
+    for (int i = 0; i < world; i++) {
+        if (ctrl->devices[i] < 0 || ctrl->devices[i] >= ndev)
+            return fail(err, errlen, ABN_ERR_ARG, "devices[%d] = %d out of range (0..%d)", i, ctrl->devices[i], ndev - 1);
+        for (int j = 0; j < i; j++)
+            if (ctrl->devices[j] == ctrl->devices[i]) return fail(err, errlen, ABN_ERR_ARG, "device %d listed twice", ctrl->devices[i]);
+    }
+    if (out->coef || out->se || out->sse)
+        return fail(err, errlen, ABN_ERR_ARG, "coef / se / sse are single-device outputs (ngpus <= 1)");
+    if (cand->rows < 0 || cand->max_parents < 0) return fail(err, errlen, ABN_ERR_ARG, "negative candidate count / width");
+    if (cand->rows > 0 && (!cand->child || (cand->max_parents > 0 && !cand->parents)))
+        return fail(err, errlen, ABN_ERR_ARG, "null candidate arrays");
+    const long long rows = cand->rows;
+    const int width = cand->max_parents;
+    const int block = ctrl->block > 0 ? ctrl->block : 1024;
+    const long long nblocks = (rows + block - 1) / block;
+
+    std::vector<int> rcs(world, ABN_OK);
+    std::vector<std::string> msgs(world);
+    auto work = [&](int rank) {
+        char lerr[512] = {0};
+        const long long mine = shard_rows(rows, block, world, rank);
+        std::vector<int32_t> child(mine), parents((size_t)mine * std::max(width, 1)), status(mine), iters(mine);
+        std::vector<double> val[4];
+        long long o = 0;
+        for (long long b = rank; b < nblocks; b += world) { // gather this device's blocks
+            const long long r0 = b * block, len = std::min<long long>(block, rows - r0);
+            std::memcpy(child.data() + o, cand->child + r0, (size_t)len * sizeof(int32_t));
+            if (width > 0) std::memcpy(parents.data() + o * width, cand->parents + r0 * width, (size_t)len * width * sizeof(int32_t));
+            o += len;
+        }
+        abn_candidates sub{mine, width, child.data(), parents.data()};
+        double *dst[4] = {out->mlik, out->aic, out->bic, out->mdl};
+        abn_result res{};
+        for (int f = 0; f < 4; f++)
+            if (dst[f]) { val[f].assign(mine, NAN); (&res.mlik)[f] = val[f].data(); }
+        res.status = status.data();
+        res.iters = iters.data();
+        abn_control lc = *ctrl;
+        lc.ngpus = 0;
+        lc.device = ctrl->devices[rank];
+        rcs[rank] = (mine > 0) ? score_cache_on(ds, &sub, &lc, lc.device, &res, lerr, sizeof(lerr)) : ABN_OK;
+        msgs[rank] = lerr;
+        if (rcs[rank] != ABN_OK) return;
+        o = 0;
+        for (long long b = rank; b < nblocks; b += world) { // scatter back into cache order
+            const long long r0 = b * block, len = std::min<long long>(block, rows - r0);
+            for (int f = 0; f < 4; f++)
+                if (dst[f]) std::memcpy(dst[f] + r0, val[f].data() + o, (size_t)len * sizeof(double));
+            if (out->status) std::memcpy(out->status + r0, status.data() + o, (size_t)len * sizeof(int32_t));
+            if (out->iters) std::memcpy(out->iters + r0, iters.data() + o, (size_t)len * sizeof(int32_t));
+            o += len;
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int r = 1; r < world; r++) threads.emplace_back(work, r);
+    work(0);
+    for (auto &t : threads) t.join();
+    for (int r = 0; r < world; r++)
+        if (rcs[r] != ABN_OK) return fail(err, errlen, rcs[r], "device %d: %s", ctrl->devices[r], msgs[r].c_str());
+    return ABN_OK;
 }
 
 extern "C" int abn_b200_last_timing(const abn_data *d, abn_timing *t)
@@ -882,4 +1077,7 @@ extern "C" void abn_b200_default_control(int32_t method, abn_control *c)
     c->solver = ABN_SOLVER_HYBRID;
     c->device = 0;
     c->nvars = 0;
+    c->ngpus = 0;                  // one device: `device`
+    c->block = 1024;
+    for (int i = 0; i < ABN_MAX_DEVICES; i++) c->devices[i] = i;
 }

@@ -163,6 +163,42 @@ ABN_HD double fast_exp256(double t, const double *tab)
     return fma(ts, p, ts);
 }
 
+// ---- exp for the lean passes, bank-conflict-free: 64-entry table, 16 interleaved replicas -------------------
+// A lane-dependent 8-byte table read costs as many shared-memory wavefronts as lanes collide on a bank pair:
+// ~9 per warp for a 256-entry table (ncu, round 2) - 40 % of all shared-memory traffic of the K = 4 Poisson
+// pass, which saturates the SM's 128 B/cycle shared-memory pipe before its FP64 pipe. Here entry j of replica
+// c = lane mod 16 sits at tab[16 j + c]: the 16 lanes of a half warp always read 16 different bank pairs, two
+// wavefronts per warp whatever the indices. 64 entries (|r| <= ln2/128) need the r^5 term back: 10 FP64
+// instructions instead of 9. Entries are pre-scaled like exp256_entry: hi(2^k 2^(j/64)) = hi(entry_j) + (n << 14).
+#define ABN_EXP64R_COPIES 16
+ABN_HD double exp64r_entry(double two_j_64, int j)
+{
+    return with_hi_word(two_j_64, hi_word(two_j_64) - (j << 14));
+}
+
+// tab_lane = table base + (lane mod 16)
+ABN_HD double fast_exp64r(double t, const double *tab_lane)
+{
+    const double MAGIC = 6755399441055744.0;        // 1.5 * 2^52
+    const double INV = 92.33245849609375;           // 64 / ln 2 to 21 bits
+    const double LN2_64_HI = 0.010830417275428772;  // 0x3f862e42 00000000
+    const double LN2_64_LO = 7.420820373486988e-09; // ln2/64 - HI
+    const double C4 = 0.041666656732559204;         // 1/24  (21 bits)
+    const double C5 = 0.00833333283662796;          // 1/120 (21 bits)
+    const double kd = fma(t, INV, MAGIC);
+    const double nf = kd - MAGIC;
+    double r = fma(nf, -LN2_64_HI, t);
+    r = fma(nf, -LN2_64_LO, r);
+    const int n = (int)(uint32_t)double_to_bits(kd);
+    double p = fma(r, C5, C4);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p * r, r, r);
+    const double tj = tab_lane[(n & 63) * ABN_EXP64R_COPIES];
+    const double ts = with_hi_word(tj, hi_word(tj) + (int)((uint32_t)n << 14));
+    return fma(ts, p, ts);
+}
+
 // 1 / d, correctly rounded for normal d with a normal result. MUFU.RCP64H seeds ~2^-20; one step
 // with cubic convergence (x (1 + e + e^2)) lands within an ulp; then Markstein's correction
 // r = fma(-d, x, 1), x + x r rounds correctly unless d's mantissa is all ones.

@@ -5,26 +5,35 @@
 
 using namespace abn;
 
-template <int KIND>
+template <int KIND, int CAPBITS>
 static cudaError_t launch_cell(const DataMeta &m, const Control &c, const FitDesc *descs, const int *child, const int *list,
                                int count, int *counter, ResultPtrs out, int sm_count, cudaStream_t stream)
 {
-    constexpr size_t smem = (size_t)CELL_WARPS * (CELL_CAP + 32) * sizeof(unsigned);
+    constexpr size_t smem = (size_t)CELL_WARPS * ((1 << CAPBITS) + 32) * sizeof(unsigned);
     static bool configured[64] = {false};
     if (first_launch_on_device(configured)) {
-        cudaError_t e = cudaFuncSetAttribute(fit_cell_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fit_cell_kernel<KIND, CAPBITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const int grid = std::min((count + CELL_WARPS - 1) / CELL_WARPS, sm_count * 2);
-    fit_cell_kernel<KIND><<<grid, CELL_WARPS * 32, smem, stream>>>(m, c, descs, child, list, count, counter, out);
+    const int per_sm = CAPBITS == CELL_SMALL_CAPBITS ? 4 : 2;
+    const int grid = std::min((count + CELL_WARPS - 1) / CELL_WARPS, sm_count * per_sm);
+    fit_cell_kernel<KIND, CAPBITS><<<grid, CELL_WARPS * 32, smem, stream>>>(m, c, descs, child, list, count, counter, out);
     return cudaGetLastError();
 }
 
-cudaError_t abn_cell_launch(int kind, const abnc::DataMeta &m, const abnc::Control &c, const abn::FitDesc *descs,
+template <int CAPBITS>
+static cudaError_t launch_cell_kind(int kind, const DataMeta &m, const Control &c, const FitDesc *descs, const int *child,
+                                    const int *list, int count, int *counter, ResultPtrs out, int sm_count, cudaStream_t stream)
+{
+    if (kind == RK_POIS) return launch_cell<RK_POIS, CAPBITS>(m, c, descs, child, list, count, counter, out, sm_count, stream);
+    if (kind == RK_BIN_BAYES) return launch_cell<RK_BIN_BAYES, CAPBITS>(m, c, descs, child, list, count, counter, out, sm_count, stream);
+    return launch_cell<RK_BIN_MLE, CAPBITS>(m, c, descs, child, list, count, counter, out, sm_count, stream);
+}
+
+cudaError_t abn_cell_launch(int kind, int large, const abnc::DataMeta &m, const abnc::Control &c, const abn::FitDesc *descs,
                             const int *child, const int *list, int count, int *counter, abnc::ResultPtrs out,
                             int sm_count, cudaStream_t stream)
 {
-    if (kind == RK_POIS) return launch_cell<RK_POIS>(m, c, descs, child, list, count, counter, out, sm_count, stream);
-    if (kind == RK_BIN_BAYES) return launch_cell<RK_BIN_BAYES>(m, c, descs, child, list, count, counter, out, sm_count, stream);
-    return launch_cell<RK_BIN_MLE>(m, c, descs, child, list, count, counter, out, sm_count, stream);
+    return large ? launch_cell_kind<CELL_LARGE_CAPBITS>(kind, m, c, descs, child, list, count, counter, out, sm_count, stream)
+                 : launch_cell_kind<CELL_SMALL_CAPBITS>(kind, m, c, descs, child, list, count, counter, out, sm_count, stream);
 }

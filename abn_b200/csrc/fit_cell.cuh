@@ -30,10 +30,13 @@
 
 namespace ABN_NS {
 
-constexpr int CELL_BITS = 12;             // log2 of the counters per warp
+// Two table sizes, two kernel instantiations: small tables leave room for twice the warps per SM (the whole
+// kernel is latency-bound: dependent shared-memory updates, a serial solver on lane 0)
+constexpr int CELL_SMALL_CAPBITS = 11;    // cell index <= 6 bits: 2 048 counters per warp (8 KB), 16 warps per SM
+constexpr int CELL_LARGE_CAPBITS = 12;    // cell index 7..10 bits: 4 096 counters per warp (16 KB), 8 warps per SM
+constexpr int CELL_SMALL_BITS = 6;
 constexpr int CELL_MAX_BITS = 10;         // widest cell index taken: at least 4 replicas per counter (<= 8 phases)
-constexpr int CELL_CAP = 1 << CELL_BITS;  // counters per warp
-constexpr int CELL_WARPS = 4;             // warps per CTA (16 KB of table each)
+constexpr int CELL_WARPS = 4;             // warps per CTA
 
 // bits needed for codes 0 .. card-1
 ABN_HD int bits_for(int card)
@@ -43,22 +46,22 @@ ABN_HD int bits_for(int card)
     return b;
 }
 
-// Is this resolved design one the cell kernel takes? (called by resolve_kernel; host builds have no byte
-// codes and never say yes)
-ABN_HD bool cell_eligible(const DataMeta &m, const FitDesc &d, int method, int flags)
+// Is this resolved design one the cell kernel takes? 0 = no, 1 = small table, 2 = large table (called by
+// resolve_kernel; host builds have no byte codes and never say yes)
+ABN_HD int cell_eligible(const DataMeta &m, const FitDesc &d, int method, int flags)
 {
-    if (m.col_card == nullptr || d.err || d.k < 1) return false;
-    if (d.family != BINOMIAL && d.family != POISSON) return false;
-    if (d.family == POISSON && method == MLE && (flags & 1)) return false; // the reference's start-value pass needs y per row
+    if (m.col_card == nullptr || d.err || d.k < 1) return 0;
+    if (d.family != BINOMIAL && d.family != POISSON) return 0;
+    if (d.family == POISSON && method == MLE && (flags & 1)) return 0; // the reference's start-value pass needs y per row
     int bits = (d.family == BINOMIAL) ? 1 : 0;                             // the response is part of a binomial cell
     for (int j = 0; j < d.k; j++) {
         if (d.cols[j] < 0) continue;
         const int card = m.col_card[d.cols[j]];
-        if (card <= 0) return false;
+        if (card <= 0) return 0;
         bits += bits_for(card);
     }
-    if (d.family == BINOMIAL && m.col_card[d.ycol] != 2) return false;
-    return bits <= CELL_MAX_BITS;
+    if (d.family == BINOMIAL && m.col_card[d.ycol] != 2) return 0;
+    return bits <= CELL_SMALL_BITS ? 1 : (bits <= CELL_MAX_BITS ? 2 : 0);
 }
 
 struct CellPlan {
@@ -70,21 +73,27 @@ struct CellPlan {
     int xslot[MAXK];     // design column j takes its value from byte column xslot[j] (-1: intercept)
 };
 
-// Contingency table of the fit: counter (cell << lc) | (lane & (copies - 1)) += 1 for every row, copies = 2^lc.
+// Contingency table of the fit. Counter of cell c: tab[(c << lc) | (set << lcl) | (lane mod copies)], copies = 2^lcl
+// replicas across lanes and 2^(lc - lcl) "sets" across consecutive rows of a lane.
 // Shared-memory atomics cost ~2 cycles per LANE on this part (the load-store unit serialises them), so the
-// counters are plain read-modify-writes instead: with 32 replicas every lane owns its counters outright; with
-// fewer, the lanes that share a replica take turns (32 / copies phases separated by __syncwarp, each phase
-// conflict-free by construction).
+// counters are plain read-modify-writes instead:
+//   * with 32 lane replicas every lane owns its counters outright; with fewer, the lanes that share a replica take
+//     turns (32 / copies phases separated by __syncwarp, each phase conflict-free by construction);
+//   * a read-modify-write is a ~35-cycle dependent chain (LDS, add, STS) and two rows of a lane may meet the same
+//     counter, so the chain cannot be overlapped - unless consecutive rows go to different sets: with 4 sets the
+//     4 counters of a row group are distinct by construction and their loads, adds and stores are issued together.
 template <int NC>
-__device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPlan &cp, unsigned *tab, int lc)
+__device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPlan &cp, unsigned *tab, int cap, int lcl, int lc)
 {
     const int lane = threadIdx.x & 31;
     const unsigned char *colp[NC];
     int sh[NC];
 #pragma unroll
     for (int j = 0; j < NC; j++) { colp[j] = m.Xq + (long long)cp.col[j] * m.ldq; sh[j] = cp.shift[j]; }
-    unsigned *const mine = tab + (lane & ((1 << lc) - 1));
-    const int nphase = 32 >> lc, my_phase = lane >> lc;
+    unsigned *const mine = tab + (lane & ((1 << lcl) - 1));
+    const int nphase = 32 >> lcl, my_phase = lane >> lcl;
+    const int nsets = 1 << (lc - lcl); // 1, 2 or 4 (only with 32 lane replicas)
+    unsigned *const dead = tab + cap + lane; // scratch counter of a lane without a row
     const long long n16 = m.n / 16;
     const long long steps = (n16 + 31) / 32; // every lane runs the same number of steps (the phases synchronise)
     // 16 rows per lane and step: one 16-byte load per column; the codes of 4 rows are combined at once when
@@ -124,19 +133,35 @@ __device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPla
         }
         if (nphase == 1) {
             if (live) {
+                if (nsets == 4) {
 #pragma unroll
-                for (int r = 0; r < 16; r++) { unsigned *p = mine + (cells[r] << lc); *p = *p + 1u; }
+                    for (int g = 0; g < 16; g += 4) {
+                        unsigned *p[4], cnt[4];
+#pragma unroll
+                        for (int t = 0; t < 4; t++) { p[t] = mine + ((cells[g + t] << lc) | (unsigned)(t << 5)); cnt[t] = *p[t]; }
+#pragma unroll
+                        for (int t = 0; t < 4; t++) *p[t] = cnt[t] + 1u;
+                    }
+                } else if (nsets == 2) {
+#pragma unroll
+                    for (int g = 0; g < 16; g += 2) {
+                        unsigned *p0 = mine + (cells[g] << lc), *p1 = mine + ((cells[g + 1] << lc) | 32u);
+                        const unsigned c0 = *p0, c1 = *p1;
+                        *p0 = c0 + 1u;
+                        *p1 = c1 + 1u;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 16; r++) { unsigned *p = mine + (cells[r] << lc); *p = *p + 1u; }
+                }
             }
         } else {
-            // a dead lane (past the last full group of 16 rows) bumps a scratch counter beyond the table
-            unsigned *const dead = tab + CELL_CAP + lane;
+            for (int ph = 0; ph < nphase; ph++) {
+                if (my_phase == ph && live) {
 #pragma unroll
-            for (int r = 0; r < 16; r++) {
-                unsigned *p = live ? mine + (cells[r] << lc) : dead;
-                for (int ph = 0; ph < nphase; ph++) {
-                    if (my_phase == ph) *p = *p + 1u;
-                    __syncwarp();
+                    for (int r = 0; r < 16; r++) { unsigned *p = mine + (cells[r] << lc); *p = *p + 1u; }
                 }
+                __syncwarp();
             }
         }
     }
@@ -148,7 +173,7 @@ __device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPla
 #pragma unroll
             for (int j = 0; j < NC; j++) cell |= (unsigned)__ldg(colp[j] + i) << sh[j];
         }
-        unsigned *p = live ? mine + (cell << lc) : tab + CELL_CAP + lane;
+        unsigned *p = live ? mine + (cell << lc) : dead;
         for (int ph = 0; ph < nphase; ph++) {
             if (my_phase == ph) *p = *p + 1u;
             __syncwarp();
@@ -257,8 +282,8 @@ __device__ __forceinline__ void cell_pass(const CellPlan &cp, const unsigned *cn
     }
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(CELL_WARPS * 32)
+template <int KIND, int CAPBITS>
+__global__ void __launch_bounds__(CELL_WARPS * 32, CAPBITS == CELL_SMALL_CAPBITS ? 4 : 2)
 fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ child,
                 const int *__restrict__ list, int count, int *counter, ResultPtrs out)
 {
@@ -268,7 +293,8 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
     __shared__ double xty_all[CELL_WARPS][MAXK];
     __shared__ double exp_tab[ABN_EXP2_N];
     __shared__ double log_tab[128];
-    extern __shared__ __align__(16) unsigned cell_tabs[]; // CELL_WARPS x (CELL_CAP counters + 32 scratch)
+    constexpr int CAP = 1 << CAPBITS;
+    extern __shared__ __align__(16) unsigned cell_tabs[]; // CELL_WARPS x (CAP counters + 32 scratch)
     if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
     if (threadIdx.x < ABN_EXP2_N) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
     __syncthreads();
@@ -277,7 +303,7 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
     PassAcc *acc = &acc_all[warp];
     CellPlan &cp = plan_all[warp];
     double *xty = xty_all[warp];
-    unsigned *tab = cell_tabs + (size_t)warp * (CELL_CAP + 32);
+    unsigned *tab = cell_tabs + (size_t)warp * (CAP + 32);
 
     for (;;) {
         int idx = 0;
@@ -305,20 +331,21 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
         }
         __syncwarp();
         const int tb = cp.total_bits;
-        const int lc = min(5, CELL_BITS - tb); // log2 of the replicas per counter
+        const int lcl = min(5, CAPBITS - tb);       // log2 of the replicas across lanes
+        const int lc = min(7, CAPBITS - tb);        // ... times the sets across rows (cell_count_rows)
         for (int i = lane; i < (1 << (tb + lc)); i += 32) tab[i] = 0u;
         __syncwarp();
         switch (cp.ncol) {
         case 0: break;
-        case 1: cell_count_rows<1>(m, cp, tab, lc); break;
-        case 2: cell_count_rows<2>(m, cp, tab, lc); break;
-        case 3: cell_count_rows<3>(m, cp, tab, lc); break;
-        case 4: cell_count_rows<4>(m, cp, tab, lc); break;
-        case 5: cell_count_rows<5>(m, cp, tab, lc); break;
-        case 6: cell_count_rows<6>(m, cp, tab, lc); break;
-        case 7: cell_count_rows<7>(m, cp, tab, lc); break;
-        case 8: cell_count_rows<8>(m, cp, tab, lc); break;
-        default: cell_count_rows<MAXK + 1>(m, cp, tab, lc); break;
+        case 1: cell_count_rows<1>(m, cp, tab, CAP, lcl, lc); break;
+        case 2: cell_count_rows<2>(m, cp, tab, CAP, lcl, lc); break;
+        case 3: cell_count_rows<3>(m, cp, tab, CAP, lcl, lc); break;
+        case 4: cell_count_rows<4>(m, cp, tab, CAP, lcl, lc); break;
+        case 5: cell_count_rows<5>(m, cp, tab, CAP, lcl, lc); break;
+        case 6: cell_count_rows<6>(m, cp, tab, CAP, lcl, lc); break;
+        case 7: cell_count_rows<7>(m, cp, tab, CAP, lcl, lc); break;
+        case 8: cell_count_rows<8>(m, cp, tab, CAP, lcl, lc); break;
+        default: cell_count_rows<MAXK + 1>(m, cp, tab, CAP, lcl, lc); break;
         }
         __syncwarp();
         // fold the replicas: counter of cell c ends up at tab[c]. Round r handles cells 32 r .. 32 r + 31: all

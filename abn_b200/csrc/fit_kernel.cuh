@@ -190,16 +190,13 @@ constexpr int FIT_STAGES = 2;
 #ifndef ABN_LEAN_STAGES
 #define ABN_LEAN_STAGES 2
 #endif
-#ifndef ABN_LEAN_DIRECT
-#define ABN_LEAN_DIRECT 0
-#endif
 // doubles of tile storage one warp needs: the staged pass (FIT_STAGES x (KD + 1) columns x 32 FIT_UNROLL rows)
 // or the lean pass (ABN_LEAN_STAGES x KD columns x 128 rows), whichever is larger
 template <int K, bool ICPT>
 constexpr size_t fit_stage_doubles_per_warp()
 {
     const size_t staged = ABN_STAGE ? (size_t)FIT_STAGES * (K - (ICPT ? 1 : 0) + 1) * 32 * FIT_UNROLL : 0;
-    const size_t lean = (ICPT && !ABN_LEAN_DIRECT) ? (size_t)ABN_LEAN_STAGES * (K - 1) * 128 : 0;
+    const size_t lean = ICPT ? (size_t)ABN_LEAN_STAGES * (K - 1) * 128 : 0;
     return staged > lean ? staged : lean;
 }
 // bytes of dynamic shared memory the passes need per CTA
@@ -619,6 +616,10 @@ __device__ __forceinline__ void warp_pass_bin(const double *__restrict__ y, cons
 //     (the rows where the reference's rho noise is visible, see warp_pass_bin), |eta| >= 700 or NaN
 //     elsewhere - returns false, and the careful pass above redoes it (and all later passes of that fit).
 //     On BASELINE-like data no fit ever does.
+//   (Measured and dropped, profiles/ab_r2_variants.txt: 16-byte read-only loads straight into registers instead of
+//   the shared-memory tiles. It halves the shared-memory traffic, but only one tile of registers fits under the
+//   128-register budget, so the loads are no longer covered: 147-152 k fits/s against 212 k, SM clocks at their
+//   maximum - the kernel waits on L2 instead of computing.)
 //   * binomial, both methods: sigma = g = 1/(1+e), e = exp(-eta); w = g - g^2; sum log(1+E) = sum log(1+e)
 //     + beta'(X'1), so the Bayes passes share the mle row op and the only per-row difference is gone.
 // Rows are summed in a fixed order that depends on nothing but n, so results stay bit-identical under any
@@ -627,6 +628,18 @@ __device__ __forceinline__ void warp_pass_bin(const double *__restrict__ y, cons
 #define ABN_LEAN 1
 #endif
 constexpr int LEAN_STAGES = ABN_LEAN_STAGES;
+// exp of the lean row ops: 1 = 64-entry table in 16 bank-interleaved replicas (fast_exp64r, 10 FP64 + 2 shared-memory
+// wavefronts), 0 = 256-entry table (fast_exp256, 9 FP64 + ~9 wavefronts)
+#ifndef ABN_EXP_REPLICATED
+#define ABN_EXP_REPLICATED 1
+#endif
+#if ABN_EXP_REPLICATED
+#define ABN_LEAN_EXP fast_exp64r
+constexpr int LEAN_EXP_DOUBLES = ABN_EXP2_N * ABN_EXP64R_COPIES;
+#else
+#define ABN_LEAN_EXP fast_exp256
+constexpr int LEAN_EXP_DOUBLES = ABN_EXP256_N;
+#endif
 constexpr int LEAN_TROWS = 128;
 
 __device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc)
@@ -699,75 +712,6 @@ __device__ __forceinline__ void lean_stream(const double *const (&cp)[MAXK], lon
     }
 }
 
-#ifndef ABN_LEAN_DIRECT
-#define ABN_LEAN_DIRECT 0
-#endif
-// Variant without shared-memory staging: 16-byte read-only loads straight into registers. The two row pairs of
-// a 128-row tile live in two register sets; each set is reloaded with its rows of the NEXT tile right after the
-// pair has been computed, so a load has the compute time of the other pair (times the warps sharing the
-// scheduler) to arrive - more than the ~250-cycle L2 latency - and only one tile of registers is ever live.
-// Same row order as lean_stream, same bits. It halves the traffic through the SM's shared-memory / L1 data
-// pipe (128 B per cycle), which the staged variant saturates before the FP64 pipe for narrow designs.
-template <int KD, typename RowFn>
-__device__ __forceinline__ void lean_stream_direct(const double *const (&cp)[MAXK], long long n, RowTrack &tk, RowFn &&row)
-{
-    constexpr int TR = LEAN_TROWS;
-    constexpr int KDA = KD > 0 ? KD : 1;
-    const int lane = threadIdx.x & 31;
-    const int ntiles = (KD > 0) ? (int)(n / TR) : 0;
-    const double2 *base[KDA];
-#pragma unroll
-    for (int j = 0; j < KD; j++) base[j] = reinterpret_cast<const double2 *>(cp[j]) + lane;
-    double2 a[KDA], b[KDA];
-    if (ntiles > 0) {
-#pragma unroll
-        for (int j = 0; j < KD; j++) { a[j] = __ldg(base[j]); b[j] = __ldg(base[j] + 32); }
-    }
-    unsigned off = 0; // in double2 units: 64 per tile
-    for (int it = 0; it < ntiles; it++) {
-        const bool more = it + 1 < ntiles;
-        off += TR / 2;
-        double x0[KDA], x1[KDA];
-#pragma unroll
-        for (int j = 0; j < KD; j++) { x0[j] = a[j].x; x1[j] = a[j].y; }
-        const int h0 = row(x0), h1 = row(x1);
-        if (more) {
-#pragma unroll
-            for (int j = 0; j < KD; j++) a[j] = __ldg(base[j] + off);
-        }
-        tk.smax = max(max(tk.smax, h0), h1);
-        tk.umax = max(max(tk.umax, (unsigned)h0), (unsigned)h1);
-#pragma unroll
-        for (int j = 0; j < KD; j++) { x0[j] = b[j].x; x1[j] = b[j].y; }
-        const int h2 = row(x0), h3 = row(x1);
-        if (more) {
-#pragma unroll
-            for (int j = 0; j < KD; j++) b[j] = __ldg(base[j] + off + 32);
-        }
-        tk.smax = max(max(tk.smax, h2), h3);
-        tk.umax = max(max(tk.umax, (unsigned)h2), (unsigned)h3);
-    }
-    for (long long i = (long long)ntiles * TR + lane; i < n; i += 32) {
-        double xt[KDA];
-#pragma unroll
-        for (int j = 0; j < KD; j++) xt[j] = __ldg(cp[j] + i);
-        const int h = row(xt);
-        tk.smax = max(tk.smax, h);
-        tk.umax = max(tk.umax, (unsigned)h);
-    }
-}
-
-template <int KD, typename RowFn>
-__device__ __forceinline__ void lean_rows(const double *const (&cp)[MAXK], long long n, double *tile, RowTrack &tk, RowFn &&row)
-{
-#if ABN_LEAN_DIRECT
-    (void)tile;
-    lean_stream_direct<KD>(cp, n, tk, row);
-#else
-    lean_stream<KD>(cp, n, tile, tk, row);
-#endif
-}
-
 // Poisson with an intercept (see warp_pass_pois for the identities). false: eta left (-700, 700), nothing written.
 template <int K, int MODE>
 __device__ __forceinline__ bool lean_pass_pois(const double *const (&cp)[MAXK], const double *beta_sm, const double *xty,
@@ -789,7 +733,7 @@ __device__ __forceinline__ bool lean_pass_pois(const double *const (&cp)[MAXK], 
         double eta = beta[0];
 #pragma unroll
         for (int j = 0; j < KD; j++) eta = fma(x[j], beta[j + 1], eta);
-        const double E = fast_exp256(eta, tab256);
+        const double E = ABN_LEAN_EXP(eta, tab256);
         H[0] += E;
         if (ALL_H) {
             int t = 1;
@@ -807,7 +751,7 @@ __device__ __forceinline__ bool lean_pass_pois(const double *const (&cp)[MAXK], 
         }
         return hi_word(eta);
     };
-    lean_rows<KD>(cp, n, tile, tk, row);
+    lean_stream<KD>(cp, n, tile, tk, row);
     if (__any_sync(0xffffffffu, (tk.smax >= 0x4085E000) | (tk.umax >= 0xC085E000u))) return false; // |eta| >= 700, NaN
 #pragma unroll
     for (int j = 0; j < NH; j++) H[j] = warp_sum(H[j]);
@@ -863,7 +807,7 @@ __device__ __forceinline__ bool lean_pass_bin(const double *const (&cp)[MAXK], c
         double eta = beta[0];
 #pragma unroll
         for (int j = 0; j < KD; j++) eta = fma(x[j], beta[j + 1], eta);
-        const double e = fast_exp256(-eta, tab256);
+        const double e = ABN_LEAN_EXP(-eta, tab256);
         const double d = 1.0 + e;
         if (NEED_L) L += fast_log_ge1(d, rc.logtab);
         if (NEED_H || NEED_G) {
@@ -889,7 +833,7 @@ __device__ __forceinline__ bool lean_pass_bin(const double *const (&cp)[MAXK], c
         }
         return hi_word(eta);
     };
-    lean_rows<KD>(cp, n, tile, tk, row);
+    lean_stream<KD>(cp, n, tile, tk, row);
     const int out_of_range = MLE_ ? ((tk.smax >= 0x40280000) | (tk.umax >= 0xC0762E42u))
                                   : ((tk.smax >= 0x4085E000) | (tk.umax >= 0xC085E000u));
     if (__any_sync(0xffffffffu, out_of_range)) return false;
@@ -959,6 +903,8 @@ __device__ __forceinline__ void run_pass(const double *__restrict__ y, const dou
 #endif
 }
 
+// `counter` points at the bucket's 16-int slot of abn_data::dCounters: [0] the work queue head, [2..15] seven
+// 64-bit tallies of the data passes by PassMode (BUCKET_SLOT_INTS in abn_b200.cu).
 // KIND: RK_BIN_MLE, RK_BIN_BAYES or RK_POIS (both methods; the mle start-value pass uses RK_PINIT)
 template <int KIND, int K, bool ICPT>
 __global__ void __launch_bounds__(FIT_WARPS * 32, ABN_MIN_BLOCKS)
@@ -971,11 +917,18 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
     __shared__ double exp_tab[ABN_EXP2_N];
     __shared__ double lnmu_tab[64];
     __shared__ double log_tab[128];
-    __shared__ double exp256_tab[ABN_EXP256_N]; // pre-scaled 2^(j/256) (fast_exp256, lean passes)
+    __shared__ double exp256_tab[LEAN_EXP_DOUBLES]; // pre-scaled exp table of the lean passes (ABN_LEAN_EXP)
     if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
     extern __shared__ __align__(16) double stage_tiles[]; // FIT_WARPS x fit_stage_doubles_per_warp
     if (threadIdx.x < ABN_EXP2_N) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
+#if ABN_EXP_REPLICATED
+    for (int i = threadIdx.x; i < LEAN_EXP_DOUBLES; i += FIT_WARPS * 32) {
+        const int j = i / ABN_EXP64R_COPIES;
+        exp256_tab[i] = exp64r_entry(c_exp2_table[j], j);
+    }
+#else
     for (int j = threadIdx.x; j < ABN_EXP256_N; j += FIT_WARPS * 32) exp256_tab[j] = exp256_entry(c_exp2_256_table[j], j);
+#endif
     if (KIND == RK_POIS && threadIdx.x < 64) lnmu_tab[threadIdx.x] = log((double)threadIdx.x + 0.1);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -983,6 +936,7 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
     PassAcc *acc = &acc_all[warp];
     double *tile = stage_tiles + (size_t)warp * fit_stage_doubles_per_warp<K, ICPT>();
     double *xty = xty_all[warp];
+    const double *lean_tab = exp256_tab + (ABN_EXP_REPLICATED ? (lane & (ABN_EXP64R_COPIES - 1)) : 0);
 
     for (;;) {
         int idx = 0;
@@ -1031,13 +985,15 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
         __syncwarp();
         int careful = 0; // set by the first lean pass that meets an eta outside its range (run_pass)
         while (mode != PASS_DONE) {
+            // passes by mode, per bucket: the numerator of the FP64 roofline (abn_timing.kernel_fp64)
+            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(counter + 2) + mode, 1ull);
             // only the modes a row kind's state machines can ask for are instantiated
-            if (mode == PASS_HG) run_pass<KIND, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
-            else if (mode == PASS_FULL) run_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
-            else if (mode == PASS_LL) run_pass<KIND, K, ICPT, PASS_LL>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
-            else if (KIND != RK_BIN_MLE && mode == PASS_GRAD) run_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
-            else if (KIND != RK_BIN_MLE && mode == PASS_HESS) run_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
-            else if (KIND == RK_POIS && mode == PASS_PINIT) run_pass<RK_PINIT, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty, exp256_tab, careful);
+            if (mode == PASS_HG) run_pass<KIND, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
+            else if (mode == PASS_FULL) run_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
+            else if (mode == PASS_LL) run_pass<KIND, K, ICPT, PASS_LL>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
+            else if (KIND != RK_BIN_MLE && mode == PASS_GRAD) run_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
+            else if (KIND != RK_BIN_MLE && mode == PASS_HESS) run_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
+            else if (KIND == RK_POIS && mode == PASS_PINIT) run_pass<RK_PINIT, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
             __syncwarp();
             if (lane == 0) mode = fit_consume(st, c, *acc);
             mode = __shfl_sync(0xffffffffu, mode, 0);

@@ -46,9 +46,10 @@ ABN_HD int bucket_of(const FitDesc &d)
     return 2 + (fam * (MAXK + 1) + d.k) * 2 + icpt;
 }
 constexpr int NBUCKETS = 2 + NFAMSLOT * (MAXK + 1) * 2;
-// all-discrete designs (fit_cell.cuh) get two buckets of their own after the streaming ones: binomial, Poisson
+// all-discrete designs (fit_cell.cuh) get four buckets of their own after the streaming ones:
+// CELL_BUCKET0 + 2 * (Poisson child) + (large table)
 constexpr int CELL_BUCKET0 = NBUCKETS;
-constexpr int NBUCKETS_ALL = NBUCKETS + 2;
+constexpr int NBUCKETS_ALL = NBUCKETS + 4;
 static_assert(MAXK > 8 || NBUCKETS_ALL <= 256, "bucket keys are bytes (the wide build does not bucket)");
 
 ABN_HD int gidx(const FitDesc &d, int j) { return d.cols[j] < 0 ? 0 : 1 + d.cols[j]; }

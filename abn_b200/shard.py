@@ -3,8 +3,8 @@
 Every (child, parent set) fit is independent (the reference already exploits this with
 ``foreach %dopar%``, R/build_score_cache_mle.R:636-681), so there is no collective inside the data
 path: each rank holds the full data set, scores an interleaved share of the candidate list, and the
-score vectors are gathered once with ``all_gather`` (NCCL over NVLink under ``torchrun``; gloo in
-the CPU tests).
+score vectors are gathered with ONE ``all_gather`` (NCCL over NVLink under ``torchrun``; gloo in the
+CPU tests).
 
 Partition: the list is cut into blocks of ``block`` consecutive candidates (neighbours share the
 child and the leading parents, which is what gives column reuse in L1/L2) and block ``b`` goes to
@@ -12,10 +12,18 @@ rank ``b % world``.  The cache order groups candidates by child (= family) and p
 contiguous split would hand one GPU all the (free) Gaussian fits; interleaving gives every rank the
 same mix.  Per-fit arithmetic does not depend on the partition, so the gathered cache is bit-identical
 to the single-GPU one.
+
+Result slab (per rank, on the device the kernels wrote it on): a ``(5, L)`` float64 tensor, 40 bytes per
+candidate - rows 0..3 are mlik / aic / bic / mdl, row 4 reinterpreted as ``2 L`` int32 holds status
+(first L) and iters (last L); ``L`` = blocks per rank (rounded up) x block.  ``abn_b200_score`` with
+``ABN_FLAG_RESULT_ON_DEVICE`` writes straight into it, ``gather_slab`` all-gathers the slabs, puts the
+blocks back in cache order with one permute on the device and makes one device-to-host copy.
 """
 from __future__ import annotations
 
 import numpy as np
+
+FIELDS = ("mlik", "aic", "bic", "mdl")
 
 
 def partition(rows: int, world: int, rank: int, block: int = 1024) -> np.ndarray:
@@ -29,38 +37,79 @@ def partition(rows: int, world: int, rank: int, block: int = 1024) -> np.ndarray
 
 
 def slab_len(rows: int, world: int, block: int = 1024) -> int:
-    """Length every rank pads its result slab to (the largest share)."""
-    return max(len(partition(rows, world, r, block)) for r in range(world)) if world > 1 else rows
-
-
-def gather(local: dict, rows: int, world: int, rank: int, block: int = 1024, device=None, group=None) -> dict:
-    """All-gather the per-rank result slabs and put them back in cache order.
-
-    `local` maps field name -> 1-D numpy array over this rank's share (float64 or int32).
-    Uses ``torch.distributed`` (must be initialised when world > 1); tensors travel on `device`
-    ("cuda:N" for NCCL, None / "cpu" for gloo).
-    """
+    """Length every rank pads its result slab to: blocks per rank (rounded up) x block."""
     if world <= 1:
-        return {k: np.asarray(v) for k, v in local.items()}
+        return rows
+    nblocks = (rows + block - 1) // block
+    return ((nblocks + world - 1) // world) * block
+
+
+def new_slab(rows: int, world: int, block: int = 1024, device=None):
+    """An empty result slab for one rank (torch tensor, float64 (5, L))."""
+    import torch
+    return torch.empty((5, slab_len(rows, world, block)), dtype=torch.float64, device=device)
+
+
+def slab_from_dict(local: dict, rows: int, world: int, block: int = 1024, device=None):
+    """Pack host results (dict of numpy arrays over this rank's share) into a slab - the host-staged path the
+    CPU tests and callers without device-resident results use."""
+    import torch
+    slab = torch.zeros((5, slab_len(rows, world, block)), dtype=torch.float64)
+    n = len(next(iter(local.values())))
+    for f, key in enumerate(FIELDS):
+        if key in local:
+            slab[f, :n] = torch.from_numpy(np.ascontiguousarray(local[key], dtype=np.float64))
+    ints = slab[4].view(torch.int32)
+    L = slab.shape[1]
+    if "status" in local:
+        ints[:n] = torch.from_numpy(np.ascontiguousarray(local["status"], dtype=np.int32))
+    if "iters" in local:
+        ints[L:L + n] = torch.from_numpy(np.ascontiguousarray(local["iters"], dtype=np.int32))
+    return slab.to(device) if device is not None else slab
+
+
+def gather_slab(slab, rows: int, world: int, block: int = 1024, group=None, to_host: bool = True):
+    """ONE all_gather of the per-rank slabs + un-interleave on the slab's device.
+
+    Returns a dict of arrays in cache order (numpy if to_host, else torch tensors on the device)."""
     import torch
     import torch.distributed as dist
 
-    L = slab_len(rows, world, block)
-    out = {}
-    for key in sorted(local):
-        v = np.asarray(local[key])
-        dtype = torch.float64 if v.dtype.kind == "f" else torch.int32
-        slab = torch.zeros(L, dtype=dtype, device=device)
-        slab[:len(v)] = torch.from_numpy(np.ascontiguousarray(v)).to(dtype).to(slab.device)
-        full = torch.empty(world * L, dtype=dtype, device=device)
-        dist.all_gather_into_tensor(full, slab, group=group)
-        full = full.cpu().numpy().reshape(world, L)
-        res = np.empty(rows, dtype=v.dtype)
-        for r in range(world):
-            idx = partition(rows, world, r, block)
-            res[idx] = full[r, :len(idx)]
-        out[key] = res
+    L = slab.shape[1]
+    if world > 1:
+        flat = torch.empty(world * 5 * L, dtype=slab.dtype, device=slab.device)
+        dist.all_gather_into_tensor(flat, slab.contiguous().reshape(-1), group=group)
+        full = flat.reshape(world, 5, L)
+    else:
+        full = slab.reshape(1, 5, L)
+    nb = L // block if world > 1 else 1
+    blk = block if world > 1 else L
+    # rank r, local block i  ->  global block i * world + r
+    dbl = full[:, :4, :].reshape(world, 4, nb, blk).permute(1, 2, 0, 3).reshape(4, nb * world * blk)[:, :rows]
+    ints = full[:, 4, :].contiguous().view(torch.int32).reshape(world, 2, nb, blk).permute(1, 2, 0, 3)
+    ints = ints.reshape(2, nb * world * blk)[:, :rows]
+    if not to_host:
+        out = {k: dbl[f] for f, k in enumerate(FIELDS)}
+        out["status"], out["iters"] = ints[0], ints[1]
+        return out
+    dbl_h = dbl.contiguous().cpu().numpy()
+    ints_h = ints.contiguous().cpu().numpy()
+    out = {k: dbl_h[f] for f, k in enumerate(FIELDS)}
+    out["status"], out["iters"] = ints_h[0], ints_h[1]
     return out
+
+
+def gather(local: dict, rows: int, world: int, rank: int, block: int = 1024, device=None, group=None) -> dict:
+    """All-gather host results (dict of numpy arrays over this rank's share) and put them back in cache
+    order. One collective for all fields; returns only the keys that were passed in."""
+    if world <= 1:
+        return {k: np.asarray(v) for k, v in local.items()}
+    slab = slab_from_dict(local, rows, world, block, device)
+    out = gather_slab(slab, rows, world, block, group=group)
+    res = {}
+    for k, v in local.items():
+        res[k] = out[k].astype(np.asarray(v).dtype, copy=False)
+    return res
 
 
 def score_sharded(score_fn, children0: np.ndarray, parents: np.ndarray, world: int, rank: int, block: int = 1024,

@@ -106,13 +106,22 @@ def make_data(n, n_nodes):
     return names, data, dists, mp, prep
 
 
-def batch_rows(total_rows, batch, block, step, rank, world):
-    """Evenly spaced blocks of `block` consecutive cache rows; different for every (step, rank)."""
+def batch_rows(total_rows, batch, block, step):
+    """One GLOBAL batch: evenly spaced blocks of `block` consecutive cache rows; different for every step."""
     nblk = max(1, batch // block)
     stride = total_rows // nblk
-    salt = (step * world + rank) * 7919 * block
+    salt = step * 7919 * block
     starts = (np.arange(nblk, dtype=np.int64) * stride + salt) % (total_rows - block)
     return (starts[:, None] + np.arange(block, dtype=np.int64)[None, :]).ravel()
+
+
+def fp64_peak():
+    """Measured DFMA ceiling of this pool's B200 (tools/fp64_peak.cu, profiles/fp64_peak_r2.json)."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r2.json")))
+        return float(rec["dfma_T_lane_fma_per_s"]), "measured (profiles/fp64_peak_r2.json: tools/fp64_peak.cu, DFMA issue rate)"
+    except Exception:
+        return 18.6, "nominal (148 SMs x 64 DFMA lanes x 1.965 GHz)"
 
 
 def main():
@@ -122,12 +131,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", default="mle", choices=["mle", "bayes"])
-    ap.add_argument("--batch", type=int, default=262144, help="fits per GPU per step (1.6 % of config 4's cache)")
+    ap.add_argument("--batch", type=int, default=2_097_152,
+                    help="fits per step over ALL GPUs (13 % of config 4's cache); strong scaling: each rank scores batch / N")
     ap.add_argument("--block", type=int, default=512)
     ap.add_argument("--rows", type=int, default=1_000_000, help="observations (BASELINE config: 1e6)")
     ap.add_argument("--nodes", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=192, help="fits in the cpu_baseline sample")
+    ap.add_argument("--side-batch", type=int, default=262_144, help="fits per step of the exact-path and bayes sub-records")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the exact-path and bayes sub-records")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -136,32 +148,44 @@ def main():
     if args.impl == "reference" and rank != 0:
         return 0
 
-    from abn_b200 import _capi as capi
-    from abn_b200 import cache as abncache
-
     t0 = time.time()
     names, data, dists, mp, prep = make_data(args.rows, args.nodes)
     d = len(names)
     P = prep.prepare(data, dists, args.method)
     zero = np.zeros((d, d), dtype=np.int32)
-    children, parents = abncache.enumerate_candidates(d, zero, zero, mp)
+    if args.impl == "reference":
+        # the reference arm touches nothing of the product: enumeration by the oracle's own restatement of buildcachematrix
+        from oracle import pyoracle
+        children1, node_defn = pyoracle.enumerate_bayes(d, zero, zero, np.full(d, mp, dtype=np.int32))
+        children = np.asarray(children1, dtype=np.int32) - (1 if np.min(children1) >= 1 else 0)
+        parents = np.full((len(children), mp), -1, dtype=np.int32)
+        rr, cc = np.nonzero(node_defn)
+        slot = np.zeros(len(children), dtype=np.int64)
+        for r, c in zip(rr, cc):  # rows are visited in order, columns ascending within a row
+            parents[r, slot[r]] = c
+            slot[r] += 1
+    else:
+        from abn_b200 import cache as abncache
+        children, parents = abncache.enumerate_candidates(d, zero, zero, mp)
     total_rows = len(children)
-    ctrl = abncache.to_c_control(abncache.build_control(args.method), args.method, d)
     setup_s = time.time() - t0
     workload = (f"synthetic {d} mixed gaussian/binomial/poisson nodes x {args.rows} rows, method={args.method}, "
-                f"max.parents={mp} ({total_rows} candidates); step = {args.batch} fits/GPU in blocks of "
+                f"max.parents={mp} ({total_rows} candidates); step = {args.batch} fits over all GPUs in blocks of "
                 f"{args.block} consecutive cache rows")
+    config = {"workload": workload, "method": args.method, "batch_fits_per_step": args.batch, "block": args.block,
+              "l2_policy": "inputs larger than L2 (800 MB matrix vs 126 MB L2); every step reads different candidate blocks"}
 
     # ------------------------------------------------------------------------------------------------
     if args.impl == "reference":
-        from oracle import pyoracle
+        from abn_b200 import cache as abncache  # control struct only (ctypes layout of include/abn_b200.h)
+        ctrl = abncache.to_c_control(abncache.build_control(args.method), args.method, d)
         threads = host_threads()
         sample = max(threads, min(args.cpu_sample, args.batch))
         times = []
         for step in range(args.warmup + args.steps):
             if step < args.warmup and step > 0:
                 continue  # one warm-up pass is enough for a CPU loop; keeps the arm within minutes
-            rows = batch_rows(total_rows, args.batch, args.block, step, 0, 1)
+            rows = batch_rows(total_rows, args.batch, args.block, step)
             rows = rows[:: max(1, len(rows) // sample)][:sample]
             t = time.perf_counter()
             pyoracle.score_cache(P.X, P.node_family, P.node_col0, children[rows], parents[rows], ctrl, threads)
@@ -169,14 +193,15 @@ def main():
                 times.append(time.perf_counter() - t)
         tot = sum(times)
         v = sample * len(times) / tot
+        sample_txt = (f"{sample} fits per step (every {max(1, args.batch // sample)}-th row of the step's {args.batch}-fit "
+                      "batch), CPU oracle (C restatement of the reference; the reference needs R+GSL+Armadillo)")
+        config["reference_sample"] = sample_txt
         line = {
             "impl": "reference", "metric": "score-cache GLM fits/sec", "value": v, "unit": "fits/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload},
-            "cpu_baseline": {"value": v, "unit": "fits/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample} fits per step, every {max(1, args.batch // sample)}-th row of the step's batch, "
-                                       "CPU oracle (C restatement of the reference; the reference needs R+GSL+Armadillo)"},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {"value": v, "unit": "fits/s", "cores": threads, "kind": "port", "sample": sample_txt},
             "e2e": {"value": v, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         _emit(line)
@@ -186,13 +211,17 @@ def main():
     import torch
     import torch.distributed as dist
 
+    from abn_b200 import _capi as capi
+    from abn_b200 import shard
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
+    devname = f"cuda:{local_rank}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist.init_process_group("nccl", device_id=torch.device(devname))
+    ctrl = abncache.to_c_control(abncache.build_control(args.method), args.method, d)
     ctrl.device = local_rank
-    from abn_b200 import shard
 
     def barrier():
         torch.cuda.synchronize()
@@ -200,23 +229,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    dev = abncache.DeviceData(P, device=local_rank)
-    launches = 0
-    kernels = {}
-    algo_bytes = 0
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=devname)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
-    def run_step(step, collect):
-        nonlocal launches, algo_bytes
-        rows = batch_rows(total_rows, args.batch, args.block, step, rank, world)
-        res = dev.score(children[rows], parents[rows], ctrl)
+    dev = abncache.DeviceData(P, device=local_rank)
+    acc = {"launches": 0, "algo_bytes": 0, "kernels": {}}
+
+    def run_step(step, collect, batch=args.batch, control=ctrl, device_data=dev):
+        """One step of the strong-scaling job: this rank scores its blocks of the global batch into a device
+        slab, ONE all_gather puts every rank's scores in cache order on the device, one copy brings them home."""
+        rows = batch_rows(total_rows, batch, args.block, step)
+        mine = rows[shard.partition(len(rows), world, rank, args.block)]
+        slab = shard.new_slab(len(rows), world, args.block, device=devname)
+        device_data.score_to_slab(children[mine], parents[mine], control, slab)
         if collect:
-            t = dev.timing()
-            launches += t["launches"]
-            algo_bytes += t["algo_bytes"]
+            t = device_data.timing()
+            acc["launches"] += t["launches"]
+            acc["algo_bytes"] += t["algo_bytes"]
             for k in t["kernels"]:
-                e = kernels.setdefault(k["name"], {"ms": 0.0, "bytes": 0, "fits": 0, "launches": 0})
-                e["ms"] += k["ms"]; e["bytes"] += k["bytes"]; e["fits"] += k["fits"]; e["launches"] += 1
-        return res
+                e = acc["kernels"].setdefault(k["name"], {"ms": 0.0, "bytes": 0, "fits": 0, "launches": 0, "fp64": 0})
+                e["ms"] += k["ms"]; e["bytes"] += k["bytes"]; e["fits"] += k["fits"]; e["launches"] += 1; e["fp64"] += k["fp64"]
+        return shard.gather_slab(slab, len(rows), world, args.block)
 
     for w in range(args.warmup):
         run_step(w, False)
@@ -226,24 +263,44 @@ def main():
     barrier()
     t1 = time.perf_counter()
     status_counts = np.zeros(3, dtype=np.int64)
-    last = None
     for s in range(args.steps):
         last = run_step(args.warmup + s, True)
         status_counts += np.bincount(last["status"], minlength=3)[:3]
     barrier()
-    elapsed = time.perf_counter() - t1
+    elapsed = max_over_ranks(time.perf_counter() - t1)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        tt = torch.tensor([elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed = float(tt.item())
-        # the one collective of the path: gather the score vectors of the last step over NVLink
-        rows_all = args.batch * world
-        gathered = shard.gather({"mlik": last["mlik"]}, rows_all, world, rank, block=args.block,
-                                device=f"cuda:{local_rank}")
-        assert len(gathered["mlik"]) == rows_all
-    fits = args.batch * args.steps * world
-    value = fits / elapsed
+    assert len(last["mlik"]) == args.batch
+    value = args.batch * args.steps / elapsed
+    launches = int(acc["launches"]) + 2 * args.steps * (1 if world > 1 else 0)  # + the gather's permute kernels
+
+    # ---- the same job with the reference's own IRLS iteration (ABN_FLAG_EXACT_PATH) and with method = bayes --------
+    extras = {}
+    if not args.no_extras:
+        def timed(batch, control, device_data, steps=2):
+            run_step(10_000, False, batch, control, device_data)
+            barrier()
+            t = time.perf_counter()
+            passes = 0
+            for s in range(steps):
+                r = run_step(10_001 + s, False, batch, control, device_data)
+                passes += int(r["iters"].sum())
+            barrier()
+            el = max_over_ranks(time.perf_counter() - t)
+            return {"value": batch * steps / el, "unit": "fits/s", "ms_per_step": 1e3 * el / steps, "steps": steps,
+                    "batch_fits_per_step": batch, "mean_passes_per_fit": passes / (batch * steps)}
+        if args.method == "mle":
+            cx = abncache.to_c_control(abncache.build_control("mle", **{"exact.path": True}), "mle", d)
+            cx.device = local_rank
+            extras["exact_path"] = timed(args.side_batch, cx, dev)
+            extras["exact_path"]["note"] = ("ABN_FLAG_EXACT_PATH: the reference's start values and stop rule pass for pass; "
+                                            "default-path figure on the same batch size beside it")
+            extras["default_path_same_batch"] = timed(args.side_batch, ctrl, dev)
+            Pb = prep.prepare(data, dists, "bayes")
+            cb = abncache.to_c_control(abncache.build_control("bayes"), "bayes", d)
+            cb.device = local_rank
+            with abncache.DeviceData(Pb, device=local_rank) as devb:
+                extras["bayes"] = timed(args.side_batch, cb, devb)
+            extras["bayes"]["note"] = "method='bayes' (Laplace mlik, GSL-hybrid iterate sequence) on the same data and cache"
 
     # ---- end to end through the one-shot C-ABI call with host buffers -------------------------------
     e2e = None
@@ -256,14 +313,16 @@ def main():
         L = capi.lib()
 
         def one_shot(step):
-            rows = batch_rows(total_rows, args.batch, args.block, step, rank, world)
+            rows = batch_rows(total_rows, args.batch, args.block, step)
+            mine = rows[shard.partition(len(rows), world, rank, args.block)]
             ds, k1 = capi.make_dataset(P2.X, P2.node_family, P2.node_col0)
             assert k1[0].ctypes.data == Xh.ctypes.data  # no hidden copy: the call reads the pinned buffer
-            cd, k2 = capi.make_candidates(children[rows], parents[rows])
+            cd, k2 = capi.make_candidates(children[mine], parents[mine])
             res, arrs = capi.make_result(cd.rows, ctrl.method)
             err = C.create_string_buffer(512)
             capi.check(L.abn_b200_score_cache(C.byref(ds), C.byref(cd), C.byref(ctrl), C.byref(res), err, len(err)), err)
-            return arrs, cd.rows * (1 + parents.shape[1]) * 4, cd.rows * (4 * 8 + 2 * 4)
+            full = shard.gather(arrs, len(rows), world, rank, args.block, device=devname)
+            return full, cd.rows * (1 + parents.shape[1]) * 4, cd.rows * (4 * 8 + 2 * 4)
 
         one_shot(0)
         barrier()
@@ -272,25 +331,24 @@ def main():
         for s in range(e_steps):
             _, cand_bytes, res_bytes = one_shot(args.warmup + s)
         barrier()
-        e_elapsed = time.perf_counter() - t2
-        if world > 1:
-            tt = torch.tensor([e_elapsed], dtype=torch.float64, device=f"cuda:{local_rank}")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e_elapsed = float(tt.item())
-        e2e = {"value": args.batch * e_steps * world / e_elapsed, "unit": "fits/s",
+        e_elapsed = max_over_ranks(time.perf_counter() - t2)
+        e2e = {"value": args.batch * e_steps / e_elapsed, "unit": "fits/s",
                "h2d_bytes_per_step": int(P.X.nbytes + cand_bytes), "d2h_bytes_per_step": int(res_bytes),
                "steps": e_steps, "ms_per_step": 1e3 * e_elapsed / e_steps,
-               "call": "abn_b200_score_cache (data upload + Gram + fits + download per step)"}
+               "call": "abn_b200_score_cache per rank (data upload + Gram + fits + download per step) + all_gather of the host results"}
 
     if rank != 0:
+        dev.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    # ---- rooflines of the dominant kernel ---------------------------------------------------------------
+    kernels = acc["kernels"]
     peak, peak_src = measured_peaks()
+    fpeak, fpeak_src = fp64_peak()
     top_name, top = max(kernels.items(), key=lambda kv: kv[1]["ms"]) if kernels else (None, None)
-    roofline = None
+    roofline = roofline_fp64 = None
     if top and top["ms"] > 0:
         per_launch_bytes = top["bytes"] / top["launches"]
         per_launch_s = top["ms"] / top["launches"] / 1e3
@@ -304,21 +362,37 @@ def main():
                                "launch under ncu --set full, scaled per fit to this launch size")
         except Exception:
             pass
+        main_ms = sum(v["ms"] for k, v in kernels.items() if v["fits"] > 4736)  # kernels on the main stream (large buckets)
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "traffic_source": traffic_src, "kernel": top_name, "peak_source": peak_src,
                     "bytes_per_launch": per_launch_bytes, "ms_per_launch": 1e3 * per_launch_s,
                     "fits_per_launch": top["fits"] / top["launches"],
-                    "kernel_share_of_fit_time": top["ms"] / sum(k["ms"] for k in kernels.values()),
+                    "kernel_share_of_main_stream_time": top["ms"] / main_ms if main_ms else None,
+                    "note": "SURVEY 8d's no-reuse streaming model; the columns are served from L2 (traffic << bytes), so this "
+                            "fraction exceeds 1 and says nothing about headroom - roofline_fp64 is the bound that binds",
                     "all_kernels": {k: {"ms": v["ms"], "GBps": (v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else None),
-                                        "fits": v["fits"]} for k, v in sorted(kernels.items())},
-                    "whole_step_GBps": algo_bytes / elapsed / 1e9, "whole_step_frac": algo_bytes / elapsed / 1e9 / peak}
+                                        "fits": v["fits"],
+                                        "fp64_T_inst_per_s": (v["fp64"] / (v["ms"] / 1e3) / 1e12 if v["ms"] > 0 and v["fp64"] else None)}
+                                    for k, v in sorted(kernels.items())},
+                    "whole_step_GBps": acc["algo_bytes"] * world / elapsed / 1e9}
+        if top["fp64"]:
+            f_ach = top["fp64"] / (top["ms"] / 1e3) / 1e12
+            step_fp64 = sum(v["fp64"] for v in kernels.values())
+            roofline_fp64 = {"bound": "fp64 pipe", "achieved": f_ach, "peak": fpeak, "unit": "T FP64 lane-instructions/s",
+                             "frac": f_ach / fpeak, "kernel": top_name, "peak_source": fpeak_src,
+                             "fp64_inst_per_launch": top["fp64"] / top["launches"],
+                             "whole_step_frac": step_fp64 / (elapsed / world) / 1e12 / fpeak / world if world == 1 else
+                             step_fp64 / elapsed / 1e12 / fpeak,
+                             "how": "per pass mode tallied on the device x rows x FP64 instructions per row counted from the "
+                                    "SASS (abn_timing.kernel_fp64), / CUDA-event kernel time / measured DFMA rate; "
+                                    "cross-check against smsp__inst_executed_pipe_fp64 in profiles/"}
 
     # ---- CPU baseline on a bounded sample of the same batch ----------------------------------------------
     cpu = None
     try:
         from oracle import pyoracle
         threads = host_threads()
-        rows = batch_rows(total_rows, args.batch, args.block, args.warmup, 0, world)
+        rows = batch_rows(total_rows, args.batch, args.block, args.warmup)
         sample = max(threads, min(args.cpu_sample, len(rows)))
         rows = rows[:: max(1, len(rows) // sample)][:sample]
         t3 = time.perf_counter()
@@ -339,16 +413,19 @@ def main():
     except Exception as e:  # pragma: no cover
         cpu = {"value": None, "unit": "fits/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
+    config.update({"setup_s": setup_s,
+                   "status_counts": {"ok": int(status_counts[0]), "not_converged": int(status_counts[1]),
+                                     "non_finite": int(status_counts[2])},
+                   "collective": "one all_gather of the 40-byte-per-fit result slabs inside the timed region" if world > 1
+                                 else "single GPU: no collective"})
     line = {
         "metric": "score-cache GLM fits/sec", "value": value, "unit": "fits/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "l2_policy": "inputs larger than L2 (800 MB matrix vs 126 MB L2); every step "
-                   "reads different candidate blocks", "setup_s": setup_s, "method": args.method,
-                   "status_counts": {"ok": int(status_counts[0]), "not_converged": int(status_counts[1]),
-                                     "non_finite": int(status_counts[2])}},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config, "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": launches, "clocks": clocks,
     }
+    line.update(extras)
     _emit(line)
     dev.close()
     if world > 1:

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ABN_B200_VERSION 100 /* 0.1.0 */
+#define ABN_B200_VERSION 200 /* 0.2.0: abn_control grew ngpus / block / devices[], abn_timing grew kernel_fp64[] */
 
 /* node families: the codes of get.var.types() (R/abn-internal.R:833) plus multinomial */
 enum {
@@ -122,6 +122,14 @@ typedef struct abn_candidates {
                                         instead of the bias-reduced irls_binomial_cpp_fast_br the score cache uses
                                         (fitAbn's first choice, R/fitabn_mle.R:585) */
 
+#define ABN_FLAG_RESULT_ON_DEVICE 4 /* abn_b200_score only: the abn_result pointers (mlik, aic, bic, mdl, status, iters; not
+                                       coef / se / sse) are DEVICE pointers on the handle's device; the kernels write the
+                                       scores there and nothing is copied to the host - the caller (e.g. one rank of a
+                                       multi-process run) hands the slab to its collective. The call still returns only
+                                       after the scores are complete. */
+
+#define ABN_MAX_DEVICES 16
+
 /* build.control() scalars that reach the natives (R/build_score_cache.R:90-127,
  * R/build_score_cache_bayes.R:314-328) */
 typedef struct abn_control {
@@ -137,6 +145,15 @@ typedef struct abn_control {
     int32_t device;     /* CUDA device ordinal this call runs on (one process per GPU)       */
     int32_t nvars;      /* MDL: number of variables in log(nvars), R/build_score_cache_mle.R:343 */
     int32_t flags;      /* ABN_FLAG_*; 0 by default                                          */
+    /* Multi-GPU, the analogue of control$ncores / cluster.type (R/build_score_cache.R:111-112, the foreach loops of
+     * R/build_score_cache_mle.R:636-681 and R/build_score_cache_bayes.R:149-193): with ngpus > 1
+     * abn_b200_score_cache runs one host thread per listed device; every device holds the whole data set and
+     * scores the blocks b = i, i + ngpus, ... of `block` consecutive candidates (block-cyclic: every device sees
+     * the cache's own mix of families and parent counts, neighbours stay together), and the scores land in the
+     * caller's arrays in cache order. Results are bit-identical to a one-device run. ngpus <= 1: `device` alone. */
+    int32_t ngpus;
+    int32_t block;      /* candidates per block of the split; 0 = 1024                       */
+    int32_t devices[ABN_MAX_DEVICES];
 } abn_control;
 
 /* Output arrays, all caller-allocated with `rows` entries; any pointer may be NULL.
@@ -234,6 +251,10 @@ typedef struct abn_timing {
     int64_t kernel_fits[ABN_MAX_KERNELS];
     int64_t kernel_bytes[ABN_MAX_KERNELS]; /* algorithmic bytes of the fits that kernel ran  */
     double kernel_ms[ABN_MAX_KERNELS];
+    int64_t kernel_fp64[ABN_MAX_KERNELS];  /* FP64 lane-instructions that kernel executed in its data passes: per pass
+                                              mode (tallied on the device) rows x the FP64 instructions one row costs
+                                              in that mode (counted from the SASS, profiles/sass_r2_*): the numerator
+                                              of bench.py's roofline_fp64. 0 for kernels without row passes.       */
 } abn_timing;
 int abn_b200_last_timing(const abn_data *d, abn_timing *t);
 

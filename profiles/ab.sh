@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for r in $(seq 1 $reps); do
 for f in abn_b200/csrc/libabn_b200.so variants/libabn_b200_*.so; do
   tag=$(basename $f .so); tag=${tag#libabn_b200_}; [ "$tag" = libabn_b200 ] && tag=default
-  ABN_B200_LIB=$PWD/$f python bench.py --steps 3 --warmup 2 --no-e2e --cpu-sample 8 "$@" > gpurun_out/ab_${tag}_$r.json 2> gpurun_out/ab_${tag}_$r.err
+  ABN_B200_LIB=$PWD/$f python bench.py --steps 3 --warmup 2 --batch 262144 --no-e2e --no-extras --cpu-sample 8 "$@" > gpurun_out/ab_${tag}_$r.json 2> gpurun_out/ab_${tag}_$r.err
   python - "$tag" gpurun_out/ab_${tag}_$r.json <<'PY'
 import json,sys
 tag,fn=sys.argv[1:3]

@@ -255,6 +255,15 @@ extern "C" void sim_fast_exp(const double *t, double *out, long n)
     for (long i = 0; i < n; i++) out[i] = fast_exp(t[i], h_exp2_table);
 }
 
+// the lean passes' exp, replicated-table form (fastmath.cuh fast_exp64r); lane 5's replica
+extern "C" void sim_fast_exp64r(const double *t, double *out, long n)
+{
+    static double tab[ABN_EXP2_N * ABN_EXP64R_COPIES];
+    static bool done = false;
+    if (!done) { for (int i = 0; i < ABN_EXP2_N * ABN_EXP64R_COPIES; i++) tab[i] = exp64r_entry(h_exp2_table[i / ABN_EXP64R_COPIES], i / ABN_EXP64R_COPIES); done = true; }
+    for (long i = 0; i < n; i++) out[i] = fast_exp64r(t[i], tab + 5);
+}
+
 // the lean passes' exp: 256-entry pre-scaled table (fastmath.cuh fast_exp256)
 extern "C" void sim_fast_exp256(const double *t, double *out, long n)
 {

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = capi.lib()
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.abn_b200_version() == 100
+    assert lib.abn_b200_version() == 200
 
 
 def test_default_control_matches_build_control():

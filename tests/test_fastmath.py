@@ -45,6 +45,23 @@ def test_fast_exp256_about_one_ulp_over_the_working_range():
     assert got[-8] == 1.0 and got[-7] == 1.0
 
 
+def test_fast_exp64r_about_one_ulp_over_the_working_range():
+    """fast_exp64r (lean passes): 64 entries in 16 bank-interleaved replicas, quintic polynomial."""
+    lib = H.sim_lib()
+    lib.sim_fast_exp64r.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_long]
+    rng = np.random.default_rng(3)
+    t = np.concatenate([rng.uniform(-700, 700, 200_000), rng.uniform(-40, 40, 200_000), rng.normal(0, 2, 200_000),
+                        np.array([0.0, -0.0, 1e-300, -1e-300, 700.0, -700.0, 36.7368005696771, -354.891356446692])])
+    got = np.empty_like(t)
+    lib.sim_fast_exp64r(t.ctypes.data_as(C.POINTER(C.c_double)), got.ctypes.data_as(C.POINTER(C.c_double)), len(t))
+    ref = np.exp(t.astype(np.longdouble))
+    ulp = np.spacing(np.exp(t))
+    err = np.abs((got.astype(np.longdouble) - ref) / ulp.astype(np.longdouble)).astype(np.float64)
+    assert err.max() < 1.5, err.max()
+    assert np.mean(err) < 0.4
+    assert got[-8] == 1.0 and got[-7] == 1.0
+
+
 def test_fast_exp_exact_points():
     got = _fast_exp(np.array([0.0, math.log(2.0) * 0]))
     assert got[0] == 1.0

@@ -533,3 +533,77 @@ def test_rank_deficient_and_near_collinear_designs_vs_oracle():
     cmp_rows = (ref["status"] != 2) & (res["status"] != 2)
     for k in ("mlik", "aic", "bic", "mdl"):
         assert H.rel_err(res[k][cmp_rows], ref[k][cmp_rows]).max() < TOL, k
+
+
+def test_result_on_device_matches_host_results():
+    """ABN_FLAG_RESULT_ON_DEVICE (the per-rank slab of abn_b200/shard.py): the kernels write into a caller-owned
+    device buffer; after the slab's own gather (world = 1: a device-side reshape + one copy) the scores are the
+    bits the host-result path returns."""
+    import torch
+    from abn_b200 import shard
+    names, data, dists, mp, _ = synth.make_config(4, n=4000, n_nodes=8)
+    d = len(names)
+    for method in ("mle", "bayes"):
+        P = prep.prepare(data, dists, method)
+        ch0, par = abncache.enumerate_candidates(d, np.zeros((d, d), int), np.zeros((d, d), int), 3)
+        ctrl = H.control(method, d)
+        with abncache.DeviceData(P) as dev:
+            host = dev.score(ch0, par, ctrl)
+            slab = shard.new_slab(len(ch0), 1, 64, device="cuda:0")
+            dev.score_to_slab(ch0, par, ctrl, slab)
+            got = shard.gather_slab(slab, len(ch0), 1, 64)
+        for k in (("mlik", "aic", "bic", "mdl") if method == "mle" else ("mlik",)):
+            assert np.array_equal(got[k], host[k], equal_nan=True), k
+        assert np.array_equal(got["status"], host["status"]) and np.array_equal(got["iters"], host["iters"])
+
+
+def test_slab_gather_unpermutes_block_cyclic_shards_on_the_device():
+    """shard.gather_slab's un-interleave, exercised without a second process: the slabs two ranks would hold are
+    built from one device's results and stacked as the all_gather would stack them."""
+    import torch
+    from abn_b200 import shard
+    names, data, dists, mp, _ = synth.make_config(4, n=3000, n_nodes=7)
+    d = len(names)
+    P = prep.prepare(data, dists, "mle")
+    ch0, par = abncache.enumerate_candidates(d, np.zeros((d, d), int), np.zeros((d, d), int), 3)
+    ctrl = H.control("mle", d)
+    rows, world, block = len(ch0), 3, 16
+    with abncache.DeviceData(P) as dev:
+        full = dev.score(ch0, par, ctrl)
+        slabs = []
+        for r in range(world):
+            idx = shard.partition(rows, world, r, block)
+            slab = shard.new_slab(rows, world, block, device="cuda:0")
+            slab.zero_()
+            dev.score_to_slab(ch0[idx], par[idx], ctrl, slab)
+            slabs.append(slab)
+    L = slabs[0].shape[1]
+    stacked = torch.stack(slabs).reshape(world, 5, L)
+    nb = L // block
+    dbl = stacked[:, :4, :].reshape(world, 4, nb, block).permute(1, 2, 0, 3).reshape(4, -1)[:, :rows].cpu().numpy()
+    for f, k in enumerate(("mlik", "aic", "bic", "mdl")):
+        assert np.array_equal(dbl[f], full[k], equal_nan=True), k
+
+
+def test_two_devices_in_one_process_are_bit_identical_to_one():
+    """abn_control.ngpus / devices (include/abn_b200.h): abn_b200_score_cache with one host thread per device.
+    Needs two GPUs (gpurun --gpus 2); also covers the per-device kernel attributes (a second device used to
+    launch without its dynamic shared memory opt-in)."""
+    if capi.lib().abn_b200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    names, data, dists, mp, _ = synth.make_config(4, n=20000, n_nodes=9)
+    d = len(names)
+    for method in ("mle", "bayes"):
+        P = prep.prepare(data, dists, method)
+        ch0, par = abncache.enumerate_candidates(d, np.zeros((d, d), int), np.zeros((d, d), int), 3)
+        one = abncache.score_cache_one_shot(P, ch0, par, H.control(method, d))
+        two = abncache.score_cache_one_shot(P, ch0, par, H.control(method, d, ngpus=2, block=64))
+        rev = abncache.score_cache_one_shot(P, ch0, par, H.control(method, d, devices=[1, 0], block=100))
+        on1 = abncache.score_cache_one_shot(P, ch0, par, H.control(method, d, devices=[1]))
+        for k in (("mlik", "aic", "bic", "mdl") if method == "mle" else ("mlik",)):
+            for other in (two, rev, on1):
+                assert np.array_equal(one[k], other[k], equal_nan=True), k
+        assert np.array_equal(one["status"], two["status"]) and np.array_equal(one["iters"], rev["iters"])
+    cache = abncache.buildScoreCache(data, dists, method="mle", max_parents=2, control={"ngpus": 2})
+    ref = abncache.buildScoreCache(data, dists, method="mle", max_parents=2)
+    assert np.array_equal(cache["mlik"], ref["mlik"], equal_nan=True)
