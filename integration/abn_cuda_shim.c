@@ -1,6 +1,6 @@
 /* The R .Call shim of INTEGRATION.md section 2 as a file: drop it into the reference's src/ next to
- * include/abn_b200.h. NOT compiled or run in this repository (no R here); the same C ABI is exercised
- * through abn_b200/_capi.py. */
+ * include/abn_b200.h. There is no R in this image, so the tests compile it against a small stand-in for R's C
+ * API (tests/r_stub/) and call both entry points the way .Call would (tests/test_r_shim.py). */
 
 /* src/abn_cuda_shim.c - .Call entry points over libabn_b200.so (include/abn_b200.h) */
 #include <R.h>
@@ -53,7 +53,16 @@ SEXP abn_cuda_score_cache(SEXP R_X, SEXP R_family, SEXP R_col0, SEXP R_children,
     const double *v = REAL(R_ctrl);
     c.max_iters = (int) v[0]; c.tol = v[1]; c.epsabs = v[2]; c.prior_mean = v[3]; c.prior_sd = v[4];
     c.gam_shape = v[5]; c.gam_scale = v[6];
-    c.nvars = asInteger(R_nvars); c.device = asInteger(R_device);
+    c.nvars = asInteger(R_nvars);
+    /* device: one ordinal, or a vector of ordinals = control$ncores' analogue: the candidate list is split over
+     * these GPUs inside the library (abn_control.ngpus / devices) */
+    const int ndev = LENGTH(R_device);
+    if (ndev < 1 || ndev > ABN_MAX_DEVICES) error("abn_b200: 1..%d devices expected", ABN_MAX_DEVICES);
+    c.device = INTEGER(R_device)[0];
+    if (ndev > 1) {
+        c.ngpus = ndev;
+        for (int i = 0; i < ndev; i++) c.devices[i] = INTEGER(R_device)[i];
+    }
     /* c.flags = ABN_FLAG_EXACT_PATH;   to follow the reference's IRLS pass for pass */
     const char *nm[] = { "mlik", "aic", "bic", "mdl", "error.code", "passes", "" };
     SEXP out = PROTECT(mkNamed(VECSXP, nm));
