@@ -116,6 +116,7 @@ EXPORTS = (
     "abn_b200_data_destroy",
     "abn_b200_score",
     "abn_b200_score_cache",
+    "abn_b200_score_enumerated",
     "abn_b200_last_timing",
 )
 
@@ -157,6 +158,10 @@ def lib() -> C.CDLL:
     L.abn_b200_score_cache.argtypes = [C.POINTER(Dataset), C.POINTER(Candidates), C.POINTER(Control),
                                        C.POINTER(Result)] + errargs
     L.abn_b200_score_cache.restype = C.c_int
+    L.abn_b200_score_enumerated.argtypes = [C.c_void_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, C.c_int32,
+                                            C.POINTER(Control), C.POINTER(Result), C.c_int64, C.c_int32,
+                                            c_int32_p, c_int32_p] + errargs
+    L.abn_b200_score_enumerated.restype = C.c_int
     L.abn_b200_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     L.abn_b200_last_timing.restype = C.c_int
     _lib = L

@@ -294,6 +294,33 @@ class DeviceData:
         del keep
         return arrs
 
+    def score_enumerated(self, banned, retained, max_parents, control: capi.Control, which_nodes=None,
+                         want_candidates: bool = True) -> dict:
+        """``abn_b200_score_enumerated``: the whole candidate list is generated on the device from the ban / retain
+        matrices (indexed [child, parent]) and scored in place - no candidate upload. Returns the score arrays and,
+        with want_candidates, ``children`` (0-based) and ``parents`` as ``enumerate_candidates`` would."""
+        L = capi.lib()
+        d = len(self.prepared.node_family)
+        ban = np.asfortranarray(banned, dtype=np.int32)
+        ret = np.asfortranarray(retained, dtype=np.int32)
+        mp = capi._i32(np.full(d, max_parents) if np.ndim(max_parents) == 0 else max_parents)
+        wn = None if which_nodes is None else capi._i32(which_nodes)
+        rows, width = C.c_int64(0), C.c_int32(0)
+        err = C.create_string_buffer(512)
+        capi.check(L.abn_b200_enumerate(d, capi.ptr_i(ban), capi.ptr_i(ret), capi.ptr_i(mp), capi.ptr_i(wn),
+                                        0 if wn is None else len(wn), C.byref(rows), C.byref(width), None, None,
+                                        err, len(err)), err)   # counts only
+        w = max(1, width.value)
+        res, arrs = capi.make_result(rows.value, control.method)
+        ch = np.empty(rows.value, dtype=np.int32) if want_candidates else None
+        pa = np.empty((rows.value, w), dtype=np.int32) if want_candidates else None
+        capi.check(L.abn_b200_score_enumerated(self._h, capi.ptr_i(ban), capi.ptr_i(ret), capi.ptr_i(mp), capi.ptr_i(wn),
+                                               0 if wn is None else len(wn), C.byref(control), C.byref(res),
+                                               rows.value, w, capi.ptr_i(ch), capi.ptr_i(pa), err, len(err)), err)
+        if want_candidates:
+            arrs["children"], arrs["parents"] = ch, pa
+        return arrs
+
     def score_to_slab(self, children0, parents, control: capi.Control, slab) -> None:
         """Scores into a device-resident result slab (abn_b200/shard.py: torch float64 (5, L) on this handle's
         device) with ABN_FLAG_RESULT_ON_DEVICE: the kernels write mlik / aic / bic / mdl / status / iters there
@@ -445,17 +472,29 @@ def buildScoreCache(data_df=None, data_dists=None, method="bayes", group_var=Non
             parents[r, :len(idx)] = idx
         children0 = ch1 - 1
     else:
+        children0 = parents = None  # enumerated below: on the device together with the fits, or on the host
+
+    cctrl = to_c_control(ctrl, method, d)
+    out = AbnCache()
+    res = None
+    if children0 is None and not dry_run and cctrl.ngpus <= 1:
+        # one call: candidates generated on the device and scored in place (abn_b200_score_enumerated)
+        with DeviceData(P, device=int(cctrl.device)) as dev:
+            res = dev.score_enumerated(banned, retained, mp, cctrl, wn_idx)
+            out.timing = dev.timing()
+        children0, parents = res.pop("children"), res.pop("parents")
+    elif children0 is None:
         children0, parents = enumerate_candidates(d, banned, retained, mp, wn_idx)
 
-    out = AbnCache()
     out["children"] = children0 + 1
     out["parents"] = parents  # compact form; "node.defn" is expanded lazily from it
     if dry_run:
         out["node.defn"] = node_defn(children0, parents, d)
         return out
 
-    cctrl = to_c_control(ctrl, method, d)
-    if cctrl.ngpus > 1:
+    if res is not None:
+        pass
+    elif cctrl.ngpus > 1:
         # control = {"ngpus": N} / {"devices": [...]}: the one-shot C-ABI call splits the list over the devices
         res = score_cache_one_shot(P, children0, parents, cctrl)
         out.timing = None

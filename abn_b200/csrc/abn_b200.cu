@@ -697,8 +697,10 @@ struct ScoreCall {
     }
 };
 
-extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn_control *ctrl, abn_result *out,
-                              char *err, size_t errlen)
+// The scoring pipeline. cand->child == NULL with resident = true: the candidates are already in d->dChild /
+// d->dParents (abn_b200_score_enumerated generated them there) - nothing is uploaded or validated.
+static int score_impl(abn_data *d, const abn_candidates *cand, bool resident, const abn_control *ctrl, abn_result *out,
+                      char *err, size_t errlen)
 {
     if (!d || !cand || !ctrl || !out) return fail(err, errlen, ABN_ERR_ARG, "null argument");
     if (cand->rows < 0 || cand->max_parents < 0) return fail(err, errlen, ABN_ERR_ARG, "negative candidate count / width");
@@ -719,7 +721,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     const int width = cand->max_parents;
     d->timing = abn_timing{};
     if (rows == 0) return ABN_OK;
-    if (!cand->child || (width > 0 && !cand->parents)) return fail(err, errlen, ABN_ERR_ARG, "null candidate arrays");
+    if (!resident && (!cand->child || (width > 0 && !cand->parents))) return fail(err, errlen, ABN_ERR_ARG, "null candidate arrays");
     CUDA_TRY(cudaSetDevice(d->device));
     PhaseTrace tr;
     int rc = ensure_scratch(d, rows, width, err, errlen);
@@ -733,8 +735,10 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     long long launches = 0;
 
     CUDA_TRY(cudaEventRecord(ev[0], s));
-    CUDA_TRY(cudaMemcpyAsync(d->dChild, cand->child, (size_t)rows * sizeof(int), cudaMemcpyHostToDevice, s));
-    if (width > 0) CUDA_TRY(cudaMemcpyAsync(d->dParents, cand->parents, (size_t)rows * width * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (!resident) {
+        CUDA_TRY(cudaMemcpyAsync(d->dChild, cand->child, (size_t)rows * sizeof(int), cudaMemcpyHostToDevice, s));
+        if (width > 0) CUDA_TRY(cudaMemcpyAsync(d->dParents, cand->parents, (size_t)rows * width * sizeof(int), cudaMemcpyHostToDevice, s));
+    }
     CUDA_TRY(cudaEventRecord(ev[1], s));
 
     Control c{ctrl->method, ctrl->max_iters, ctrl->solver, ctrl->nvars, ctrl->tol, ctrl->epsabs,
@@ -770,11 +774,14 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     CUDA_TRY(cudaMemcpyAsync(dFirstBad, &int_max, sizeof(int), cudaMemcpyHostToDevice, s));
 
     const int tb = 128;
-    validate_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(rows, width, d->m.n_nodes, d->dChild, d->dParents, dFirstBad);
-    KCHECK("validate_kernel", s);
     int first_bad = int_max;
-    CUDA_TRY(cudaMemcpyAsync(&first_bad, dFirstBad, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    if (!resident) {
+        validate_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(rows, width, d->m.n_nodes, d->dChild, d->dParents, dFirstBad);
+        KCHECK("validate_kernel", s);
+        CUDA_TRY(cudaMemcpyAsync(&first_bad, dFirstBad, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        launches++;
+    }
     if (first_bad != int_max) {
         const long long r = first_bad;
         const int ch = cand->child[r];
@@ -795,7 +802,7 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     KCHECK("radix sort", s);
     bucket_bounds<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(d->dKeysSorted, rows, d->dBucketStart);
     KCHECK("bucket_bounds", s);
-    launches += 4;
+    launches += 3;
     int hstart[NBUCKETS_ALL + 1];
     CUDA_TRY(cudaMemcpyAsync(hstart, d->dBucketStart, sizeof(hstart), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -949,6 +956,161 @@ extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn
     if (n_unsupported > 0 && n_unsupported == rows)
         return fail(err, errlen, ABN_ERR_LIMIT, "no candidate could be scored by the fast kernels");
     return ABN_OK;
+}
+
+extern "C" int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn_control *ctrl, abn_result *out,
+                              char *err, size_t errlen)
+{
+    return score_impl(d, cand, false, ctrl, out, err, errlen);
+}
+
+// ---------------------------------------------------------------------------------------------
+// candidate enumeration on the device: the list of abn_b200_enumerate, row r computed from r
+// ---------------------------------------------------------------------------------------------
+struct EnumNode {
+    int child, n_free, n_must, jmax;
+    long long row0; // first row of this node in the list
+};
+
+// Row r of the list: node by binary search over row0, parent count j by the node's per-size offsets, then
+// the (r - offset)-th (j - n_must)-subset of the node's free parents in lexicographic order (combinatorial
+// unranking with a binomial table), merged with the retained parents. A subset that contains the retained
+// parents precedes another one exactly when its free part does (the smallest element of the symmetric
+// difference decides either comparison), so this is the order buildcachematrix visits the survivors in.
+__global__ void enumerate_kernel(long long rows, int n_list, int d, int W, const EnumNode *__restrict__ nodes,
+                                 const long long *__restrict__ size_row0 /* [n_list][W + 2] */,
+                                 const int *__restrict__ free_list, const int *__restrict__ must_list,
+                                 const unsigned long long *__restrict__ binom /* [d + 1][W + 1] */,
+                                 int *__restrict__ child, int *__restrict__ parents)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int lo = 0, hi = n_list - 1;
+    while (lo < hi) { // last node with row0 <= r
+        const int mid = (lo + hi + 1) >> 1;
+        if (nodes[mid].row0 <= r) lo = mid; else hi = mid - 1;
+    }
+    const EnumNode nd = nodes[lo];
+    const long long *off = size_row0 + (long long)lo * (W + 2);
+    int j = 0;
+    while (j < nd.jmax && off[j + 1] <= r) j++;
+    unsigned long long q = (unsigned long long)(r - off[j]);
+    const int t = j - nd.n_must; // free parents to choose
+    const int *fl = free_list + (long long)lo * d, *ml = must_list + (long long)lo * d;
+    int *row = parents + r * W;
+    int x = 0, mi = 0, o = 0;
+    for (int i = 0; i < t; i++) {
+        for (;;) { // subsets that start with free[x] at position i: C(n_free - x - 1, t - i - 1)
+            const unsigned long long c = binom[(long long)(nd.n_free - x - 1) * (W + 1) + (t - i - 1)];
+            if (q < c) break;
+            q -= c;
+            x++;
+        }
+        const int p = fl[x++];
+        while (mi < nd.n_must && ml[mi] < p) row[o++] = ml[mi++];
+        row[o++] = p;
+    }
+    while (mi < nd.n_must) row[o++] = ml[mi++];
+    while (o < W) row[o++] = -1;
+    child[r] = nd.child;
+}
+
+extern "C" int abn_b200_score_enumerated(abn_data *d, const int32_t *banned, const int32_t *retained,
+                                         const int32_t *max_parents, const int32_t *which_nodes, int32_t n_which,
+                                         const abn_control *ctrl, abn_result *out, int64_t rows_expected, int32_t width,
+                                         int32_t *children, int32_t *parents, char *err, size_t errlen)
+{
+    if (!d || !max_parents || !ctrl || !out) return fail(err, errlen, ABN_ERR_ARG, "null argument");
+    if ((children == nullptr) != (parents == nullptr)) return fail(err, errlen, ABN_ERR_ARG, "children and parents must be given together");
+    const int dn = d->m.n_nodes;
+    const int n_list = which_nodes ? n_which : dn;
+    // per listed node: free and retained parents (ascending), rows per parent count - O(n_list x d) host work
+    int W = 0;
+    for (int w = 0; w < n_list; w++) {
+        const int node = which_nodes ? which_nodes[w] : w;
+        if (node < 0 || node >= dn) return fail(err, errlen, ABN_ERR_ARG, "which_nodes[%d] = %d out of range", w, node);
+        if (max_parents[node] < 0) return fail(err, errlen, ABN_ERR_ARG, "max_parents[%d] < 0", node);
+        W = std::max(W, std::min<int>(max_parents[node], dn));
+    }
+    if (width < W) return fail(err, errlen, ABN_ERR_ARG, "width %d too small, need %d", width, W);
+    const int rowW = std::max(width, 1);
+    std::vector<unsigned long long> binom((size_t)(dn + 1) * (rowW + 1), 0ull);
+    for (int m = 0; m <= dn; m++)
+        for (int t = 0; t <= rowW; t++) {
+            unsigned long long v = (t == 0) ? 1ull : ((m == 0) ? 0ull : binom[(size_t)(m - 1) * (rowW + 1) + t - 1] + binom[(size_t)(m - 1) * (rowW + 1) + t]);
+            binom[(size_t)m * (rowW + 1) + t] = std::min(v, 1ull << 62); // saturate: such lists are refused below anyway
+        }
+    std::vector<EnumNode> nodes;
+    std::vector<long long> size_row0;
+    std::vector<int> free_list, must_list;
+    long long total = 0;
+    for (int w = 0; w < n_list; w++) {
+        const int node = which_nodes ? which_nodes[w] : w;
+        std::vector<int> fr, mu;
+        bool impossible = false;
+        for (int p = 0; p < dn; p++) {
+            const bool ban = banned && banned[node + (long long)p * dn] == 1;
+            const bool ret = retained && retained[node + (long long)p * dn] == 1;
+            if (ret && (p == node || ban)) impossible = true; // a retained arc that can never be present
+            if (ret) mu.push_back(p);
+            else if (p != node && !ban) fr.push_back(p);
+        }
+        if (impossible) continue;
+        EnumNode e{node, (int)fr.size(), (int)mu.size(), std::min<int>(max_parents[node], dn), total};
+        std::vector<long long> off(rowW + 2, 0);
+        for (int j = 0; j <= rowW; j++) {
+            off[j] = total;
+            if (j <= e.jmax && j >= e.n_must && j - e.n_must <= e.n_free)
+                total = std::min<long long>(total + (long long)binom[(size_t)e.n_free * (rowW + 1) + (j - e.n_must)], 1ll << 62);
+        }
+        off[rowW + 1] = total;
+        if (total == e.row0) continue; // no candidate for this node
+        nodes.push_back(e);
+        size_row0.insert(size_row0.end(), off.begin(), off.end());
+        fr.resize(dn, -1);
+        mu.resize(dn, -1);
+        free_list.insert(free_list.end(), fr.begin(), fr.end());
+        must_list.insert(must_list.end(), mu.begin(), mu.end());
+    }
+    if (total != rows_expected)
+        return fail(err, errlen, ABN_ERR_ARG, "the enumeration has %lld rows, the caller expects %lld (abn_b200_enumerate reports the count)",
+                    total, (long long)rows_expected);
+    d->timing = abn_timing{};
+    if (total == 0) return ABN_OK;
+    if (total > 2000000000LL) return fail(err, errlen, ABN_ERR_LIMIT, "more than 2e9 candidates in one call; split the list");
+    CUDA_TRY(cudaSetDevice(d->device));
+    int rc = ensure_scratch(d, total, rowW, err, errlen);
+    if (rc != ABN_OK) return rc;
+    {
+        ScoreCall call(d);
+        cudaStream_t s = d->stream;
+        EnumNode *dNodes = nullptr;
+        long long *dOff = nullptr;
+        int *dFree = nullptr, *dMust = nullptr;
+        unsigned long long *dBinom = nullptr;
+        CUDA_TRY(call.alloc(&dNodes, nodes.size() * sizeof(EnumNode)));
+        CUDA_TRY(call.alloc(&dOff, size_row0.size() * sizeof(long long)));
+        CUDA_TRY(call.alloc(&dFree, free_list.size() * sizeof(int)));
+        CUDA_TRY(call.alloc(&dMust, must_list.size() * sizeof(int)));
+        CUDA_TRY(call.alloc(&dBinom, binom.size() * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemcpyAsync(dNodes, nodes.data(), nodes.size() * sizeof(EnumNode), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(dOff, size_row0.data(), size_row0.size() * sizeof(long long), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(dFree, free_list.data(), free_list.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(dMust, must_list.data(), must_list.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(dBinom, binom.data(), binom.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        enumerate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(total, (int)nodes.size(), dn, rowW, dNodes, dOff, dFree, dMust,
+                                                                      dBinom, d->dChild, d->dParents);
+        KCHECK("enumerate_kernel", s);
+        if (children) {
+            CUDA_TRY(cudaMemcpyAsync(children, d->dChild, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(parents, d->dParents, (size_t)total * rowW * sizeof(int), cudaMemcpyDeviceToHost, s));
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    abn_candidates cand{total, rowW, nullptr, nullptr};
+    rc = score_impl(d, &cand, true, ctrl, out, err, errlen);
+    d->timing.launches += 1;
+    return rc;
 }
 
 static int score_cache_on(const abn_dataset *ds, const abn_candidates *cand, const abn_control *ctrl, int device,

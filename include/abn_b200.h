@@ -227,6 +227,21 @@ void abn_b200_data_destroy(abn_data *d);
 int abn_b200_score(abn_data *d, const abn_candidates *cand, const abn_control *ctrl,
                    abn_result *out, char *err, size_t errlen);
 
+/*
+ * A whole cache without a candidate upload: the list abn_b200_enumerate describes is generated on the
+ * device - row r from r, by combinatorial unranking over the node's admissible parents - and scored in place, so
+ * that only the d x d ban / retain matrices travel to the GPU (config 4: 260 MB of indices otherwise). Arguments as
+ * for abn_b200_enumerate; `rows` and `width` are what that function reports (call it with children == NULL first:
+ * it only counts), the output arrays of `out` have `rows` entries. children / parents (optional, both or neither,
+ * host memory, same layout as abn_b200_enumerate fills) receive the list for the abnCache's children / node.defn.
+ * Bit-identical to abn_b200_enumerate + abn_b200_score. Replaces buildcachematrix()'s gsl_combination walk
+ * (src/buildcachematrix.c:41-130) together with the loops over its result.
+ */
+int abn_b200_score_enumerated(abn_data *d, const int32_t *banned, const int32_t *retained,
+                              const int32_t *max_parents, const int32_t *which_nodes, int32_t n_which,
+                              const abn_control *ctrl, abn_result *out, int64_t rows, int32_t width,
+                              int32_t *children, int32_t *parents, char *err, size_t errlen);
+
 /* one-shot: data_create + score + data_destroy */
 int abn_b200_score_cache(const abn_dataset *ds, const abn_candidates *cand,
                          const abn_control *ctrl, abn_result *out, char *err, size_t errlen);

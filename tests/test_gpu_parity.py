@@ -607,3 +607,48 @@ def test_two_devices_in_one_process_are_bit_identical_to_one():
     cache = abncache.buildScoreCache(data, dists, method="mle", max_parents=2, control={"ngpus": 2})
     ref = abncache.buildScoreCache(data, dists, method="mle", max_parents=2)
     assert np.array_equal(cache["mlik"], ref["mlik"], equal_nan=True)
+
+
+def _enum_boundary_cases():
+    import test_boundary as TB
+    return TB._enum_cases()
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_device_enumeration_is_bit_exact_on_the_boundary_cases(case):
+    """abn_b200_score_enumerated: the list generated on the device row by row equals
+    abn_b200_enumerate's (itself bit-exact with the reference algorithm, tests/test_boundary.py) on bans, retained
+    arcs, per-node limits and which.nodes; the scores equal those of the uploaded list bit for bit."""
+    d, ban, ret, mp, wn = _enum_boundary_cases()[case]
+    fams = (["gaussian", "binomial", "poisson"] * 3)[:d]
+    names, data, dists = synth.make_columns(500, fams, seed=11)
+    P = prep.prepare(data, dists, "bayes")
+    ch, par = abncache.enumerate_candidates(d, ban, ret, mp, wn)
+    ctrl = H.control("bayes", d)
+    with abncache.DeviceData(P) as dev:
+        got = dev.score_enumerated(ban, ret, mp, ctrl, wn)
+        ref = dev.score(ch, par, ctrl) if len(ch) else None
+    assert np.array_equal(got["children"], ch)
+    assert np.array_equal(got["parents"][:, :par.shape[1]], par) and (got["parents"][:, par.shape[1]:] == -1).all()
+    if ref is not None:
+        assert np.array_equal(got["mlik"], ref["mlik"], equal_nan=True) and np.array_equal(got["status"], ref["status"])
+
+
+def test_device_enumeration_reproduces_the_golden_lists():
+    """ex1 (2 560 rows, max.parents = 4) and mycache.c2 (56 458 rows, banned arcs): children / parents of the
+    reference's own caches from the device enumeration; buildScoreCache takes this path by default."""
+    z = H.load_npz("ex1_bayes.npz")
+    names, data = H.df_from_npz(z)
+    dists = H.dists_from_npz(z)
+    P = prep.prepare(data, dists, "bayes")
+    zero = np.zeros((10, 10), int)
+    with abncache.DeviceData(P) as dev:
+        got = dev.score_enumerated(zero, zero, 4, H.control("bayes", 10))
+    assert np.array_equal(got["children"] + 1, z["children"]) and np.array_equal(got["parents"], z["parents"])
+    assert H.rel_err(got["mlik"], z["mlik"]).max() < 1e-9
+    z2 = H.load_npz("c2_bayes.npz")
+    names2, data2 = H.df_from_npz(z2)
+    cache = abncache.buildScoreCache(data2, H.dists_from_npz(z2), method="bayes", max_parents=int(np.max(z2["max_par"])),
+                                     dag_banned=z2["banned"], dag_retained=z2["retained"])
+    assert np.array_equal(cache["children"], z2["children"])
+    assert np.array_equal(cache.status, z2["error_code"])
