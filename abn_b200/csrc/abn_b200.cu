@@ -151,11 +151,11 @@ static bool debug_sync()
 constexpr int GT = 6;        // register tile edge
 constexpr int GRAM_THREADS = 256;
 
-// value of Gram column a at row i
-__device__ __forceinline__ double z_value(const DataMeta &m, int a, long long i)
+// value of Gram column a at row i; `shift` (optional, [1 + n_cols], shift[0] = 0) is subtracted: the centred Gram
+__device__ __forceinline__ double z_value(const DataMeta &m, int a, long long i, const double *__restrict__ shift)
 {
     if (a == 0) return 1.0;
-    if (a <= m.n_cols) return __ldg(m.X + (long long)(a - 1) * m.ld + i);
+    if (a <= m.n_cols) return __ldg(m.X + (long long)(a - 1) * m.ld + i) - (shift ? shift[a] : 0.0);
     const int node = m.pois_node[a - 1 - m.n_cols]; // virtual column: log(y + 0.1) of a Poisson node (Bayes start values)
     return log(__ldg(m.X + (long long)m.node_col0[node] * m.ld + i) + 0.1);
 }
@@ -166,7 +166,7 @@ __device__ __forceinline__ double z_value(const DataMeta &m, int a, long long i)
 // part[chunk][pair][GT*GT]; gram_reduce sums the chunks in a fixed order.
 __global__ void __launch_bounds__(GRAM_THREADS)
 gram_partial(const DataMeta m, int Dz, int T, int NP, int RC, int Dp, long long rows_per_chunk,
-             double *__restrict__ part)
+             double *__restrict__ part, const double *__restrict__ shift)
 {
     extern __shared__ double zs[]; // RC x Dp
     const int pair = blockIdx.y * GRAM_THREADS + threadIdx.x;
@@ -193,7 +193,7 @@ gram_partial(const DataMeta m, int Dz, int T, int NP, int RC, int Dp, long long 
         // 64-bit loads. Columns past Dz in the last tile are staged as zeros.
         for (int e = threadIdx.x; e < RC * T * GT; e += GRAM_THREADS) {
             const int col = e / RC, r = e - col * RC;
-            zs[r * Dp + (col / GT) * (GT + 1) + col % GT] = (col < Dz && r < nr) ? z_value(m, col, base + r) : 0.0;
+            zs[r * Dp + (col / GT) * (GT + 1) + col % GT] = (col < Dz && r < nr) ? z_value(m, col, base + r, shift) : 0.0;
         }
         __syncthreads();
         if (pair < NP) {
@@ -234,6 +234,13 @@ __global__ void gram_reduce(int D, int T, int NP, int chunks, const double *__re
     for (int c = 0; c < chunks; c++) s += part[((long long)c * NP + pair) * (GT * GT) + st];
     G[(long long)i * D + j] = s;
     G[(long long)j * D + i] = s;
+}
+
+// shift[0] = 0, shift[1 + j] = mean of stored column j = G[0][1 + j] / n
+__global__ void col_mean_kernel(int n_cols, int D, double n, const double *__restrict__ G, double *__restrict__ shift)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a <= n_cols) shift[a] = (a == 0) ? 0.0 : G[a] / n;
 }
 
 // sum lgamma(y + 1) per Poisson node (src/irls_poisson_fast.cpp:32-34, gsl_sf_lnfact in
@@ -351,12 +358,12 @@ gauss_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ desc
     const int row = list[t];
     const FitDesc d = descs[row];
     if (c.method == MLE) {
-        double ll, aic, bic, x[MAXM], se[MAXM];
+        double ll, aic, bic, x[MAXM], se[MAXM], sse;
         int status;
-        gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x, out.se ? se : nullptr);
+        gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x, out.se ? se : nullptr, &sse);
         write_coef(out, row, d, x, d.k);
         if (out.se) { ResultPtrs o = out; o.coef = out.se; write_coef(o, row, d, se, d.k); }
-        if (out.sse) out.sse[row] = sse_of(m, d, x);
+        if (out.sse) out.sse[row] = sse;
         if (out.mlik) out.mlik[row] = ll;
         if (out.aic) out.aic[row] = aic;
         if (out.bic) out.bic[row] = bic;
@@ -367,7 +374,9 @@ gauss_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ desc
     }
     FitState s;
     PassAcc a;
+    GaussAux aux;
     state_setup(m, d, child[row], c, s);
+    if (gauss_centered_block(m, d, aux)) s.gaux = &aux;
     bayes_inits(m, d, child[row], s);
     gauss_gram_acc(m, d, a);
     int mode = fit_begin(s, c);
@@ -388,6 +397,7 @@ struct abn_data {
     int *dFamily = nullptr, *dCol0 = nullptr, *dGwIndex = nullptr, *dPoisNode = nullptr;
     unsigned char *dXq = nullptr; // byte codes of the discrete columns (fit_cell.cuh)
     int *dColCard = nullptr;
+    double *dGc = nullptr, *dColMean = nullptr; // centred Gram and the shifts it was built with ([0] = 0)
     std::vector<int> family, col0, gw_index;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -425,6 +435,7 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
     dev_free(d->dX, d->stream); dev_free(d->dG, d->stream); dev_free(d->dLfact, d->stream); dev_free(d->dFamily, d->stream); dev_free(d->dCol0, d->stream);
     dev_free(d->dGwIndex, d->stream); dev_free(d->dPoisNode, d->stream);
     dev_free(d->dXq, d->stream); dev_free(d->dColCard, d->stream);
+    dev_free(d->dGc, d->stream); dev_free(d->dColMean, d->stream);
     dev_free(d->dBucketStart, d->stream); dev_free(d->dCounters, d->stream);
     cudaStreamSynchronize(d->stream); // the frees above are stream-ordered
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -434,7 +445,7 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
 }
 
 // G = Z'Z over the Dz columns of Z, result Dz x Dz at dst
-static int launch_gram(abn_data *d, int Dz, double *dst, char *err, size_t errlen)
+static int launch_gram(abn_data *d, int Dz, double *dst, const double *shift, char *err, size_t errlen)
 {
     const DataMeta &m = d->m;
     const int T = (Dz + GT - 1) / GT;
@@ -456,7 +467,7 @@ static int launch_gram(abn_data *d, int Dz, double *dst, char *err, size_t errle
     const size_t smem = (size_t)RC * Dp * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
     if (e == cudaSuccess) {
-        gram_partial<<<dim3(chunks, gy), GRAM_THREADS, smem, d->stream>>>(m, Dz, T, NP, RC, Dp, rpc, part);
+        gram_partial<<<dim3(chunks, gy), GRAM_THREADS, smem, d->stream>>>(m, Dz, T, NP, RC, Dp, rpc, part, shift);
         gram_reduce<<<(NP * GT * GT + 255) / 256, 256, 0, d->stream>>>(Dz, T, NP, chunks, part, dst);
         e = cudaStreamSynchronize(d->stream);
     }
@@ -470,8 +481,18 @@ static int launch_gram(abn_data *d, int Dz, double *dst, char *err, size_t errle
 static int compute_gram(abn_data *d, char *err, size_t errlen)
 {
     const DataMeta &m = d->m;
-    int rc = launch_gram(d, m.D, d->dG, err, errlen);
+    int rc = launch_gram(d, m.D, d->dG, nullptr, err, errlen);
     if (rc != ABN_OK) return rc;
+    // centred second moments for the Gaussian children: column means from the raw Gram, then the Gram of
+    // [1 | X - mean] (types.cuh DataMeta::Gc)
+    if (d->dGc) {
+        col_mean_kernel<<<(m.n_cols + 1 + 127) / 128, 128, 0, d->stream>>>(m.n_cols, m.D, (double)m.n, d->dG, d->dColMean);
+        rc = launch_gram(d, 1 + m.n_cols, d->dGc, d->dColMean, err, errlen);
+        if (rc != ABN_OK) return rc;
+        d->timing.launches += 1;
+        d->m.Gc = d->dGc;
+        d->m.col_mean = d->dColMean + 1;
+    }
     lfact_kernel<<<m.n_nodes, 256, 0, d->stream>>>(m, d->dLfact);
     d->timing.launches += 1;
     CUDA_TRY(cudaStreamSynchronize(d->stream));
@@ -536,6 +557,12 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     TRY_OR_FREE(dev_alloc(&d->dX, (size_t)ld * ds->n_cols * sizeof(double), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dG, (size_t)D * D * sizeof(double), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dLfact, (size_t)ds->n_nodes * sizeof(double), d->stream));
+    bool any_gaussian = false;
+    for (int i = 0; i < ds->n_nodes; i++) any_gaussian |= ds->node_family[i] == ABN_GAUSSIAN;
+    if (any_gaussian) {
+        TRY_OR_FREE(dev_alloc(&d->dGc, (size_t)(1 + ds->n_cols) * (1 + ds->n_cols) * sizeof(double), d->stream));
+        TRY_OR_FREE(dev_alloc(&d->dColMean, (size_t)(1 + ds->n_cols) * sizeof(double), d->stream));
+    }
     TRY_OR_FREE(dev_alloc(&d->dFamily, (size_t)ds->n_nodes * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dCol0, (size_t)(ds->n_nodes + 1) * sizeof(int), d->stream));
     TRY_OR_FREE(dev_alloc(&d->dGwIndex, (size_t)ds->n_nodes * sizeof(int), d->stream));
@@ -576,6 +603,8 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     d->m.Xq = nullptr;
     d->m.ldq = ld;
     d->m.col_card = nullptr;
+    d->m.Gc = nullptr;
+    d->m.col_mean = nullptr;
     if (d->dXq) {
         int *bad = d->dColCard + ds->n_cols, *mx = d->dColCard + 2 * ds->n_cols;
         cudaError_t e = cudaMemsetAsync(d->dColCard, 0, (size_t)ds->n_cols * 3 * sizeof(int), d->stream);

@@ -131,6 +131,33 @@ ABN_HDN void resolve_design(const DataMeta &m, int method, int child, const int 
     }
 }
 
+// ---- centred moments (DataMeta::Gc) ---------------------------------------------------------------
+ABN_HD double gc_at(const DataMeta &m, int gi, int gj) { return m.Gc[(long long)gi * (1 + m.n_cols) + gj]; }
+// sum (z_a - mean_a)(z_b - mean_b) for Gram indices a, b >= 1 (Gc is centred at col_mean, which is the true mean
+// up to its rounding; the last term removes what is left)
+ABN_HD double cmom(const DataMeta &m, int ga, int gb)
+{
+    return gc_at(m, ga, gb) - gc_at(m, 0, ga) * gc_at(m, 0, gb) / (double)m.n;
+}
+ABN_HD double cmean(const DataMeta &m, int ga) { return m.col_mean[ga - 1] + gc_at(m, 0, ga) / (double)m.n; }
+
+// Centred blocks of a Gaussian child's design, when they apply: centred moments present, intercept in column 0.
+ABN_HD bool gauss_centered_block(const DataMeta &m, const FitDesc &d, GaussAux &g)
+{
+    if (m.Gc == nullptr || d.k < 1 || d.cols[0] >= 0) return false;
+    const int k1 = d.k - 1, gy = gram_col(d.ycol);
+    g.k1 = k1;
+    for (int i = 0; i < k1; i++) {
+        const int gi = gidx(d, 1 + i);
+        for (int j = 0; j < k1; j++) A_(g.Cxx, i, j) = cmom(m, gi, gidx(d, 1 + j));
+        g.Cxy[i] = cmom(m, gi, gy);
+        g.xbar[i] = cmean(m, gi);
+    }
+    g.Cyy = cmom(m, gy, gy);
+    g.ybar = cmean(m, gy);
+    return true;
+}
+
 // Standard errors as fitAbn(method = "mle") derives them from the `varcov` its IRLS functions return
 // (R/fitabn_mle.R:715-745): se_i = sqrt(scale * inv(V)_ii) with V = X'WX of the last iteration (binomial,
 // Poisson; scale = 1) or X'X (Gaussian; scale = mse = sse / (n - k)). V is MAXM-strided; NaN if singular.
@@ -152,23 +179,35 @@ ABN_HDN void se_from_information(const double *V, int k, double scale, double *s
 
 // ---- Gaussian child, method = "mle": src/irls_gaussian_fast.cpp:34-49 from Gram blocks ---------
 ABN_HDN void gauss_mle_fit(const DataMeta &m, const FitDesc &d, double *loglik, double *aic, double *bic, int *status,
-                           double *coef = nullptr, double *se = nullptr)
+                           double *coef = nullptr, double *se = nullptr, double *sse = nullptr)
 {
     const int k = d.k;
     double A[MAXM * MAXM], S[MAXM * MAXM], b[MAXM], x[MAXM];
     gram_block(m, d, 0, k, A);
     const long long gy = gram_col(d.ycol);
     for (int i = 0; i < k; i++) b[i] = m.G[(long long)gidx(d, i) * m.D + gy];
-    int st = sym_solve(A, b, k, true, x, S);
-    double yy = m.G[gy * m.D + gy];
-    double xb = 0.0, xax = 0.0;
-    for (int i = 0; i < k; i++) {
-        double t = 0.0;
-        for (int j = 0; j < k; j++) t += A_(A, i, j) * x[j];
-        xax += t * x[i];
-        xb += b[i] * x[i];
+    int st;
+    double ssr;
+    GaussAux g;
+    if (d.rank == k && gauss_centered_block(m, d, g)) {
+        // full-rank design with an intercept: slopes from the centred normal equations, intercept from the means;
+        // the residual sum of squares is formed from centred moments (no cancellation against n * mean(y)^2)
+        st = sym_solve(g.Cxx, g.Cxy, g.k1, true, x + 1, S);
+        x[0] = g.ybar;
+        for (int i = 0; i < g.k1; i++) x[0] -= x[1 + i] * g.xbar[i];
+        ssr = gauss_aux_rss(g, x, (double)m.n);
+    } else {
+        st = sym_solve(A, b, k, true, x, S);
+        double yy = m.G[gy * m.D + gy];
+        double xb = 0.0, xax = 0.0;
+        for (int i = 0; i < k; i++) {
+            double t = 0.0;
+            for (int j = 0; j < k; j++) t += A_(A, i, j) * x[j];
+            xax += t * x[i];
+            xb += b[i] * x[i];
+        }
+        ssr = yy - 2.0 * xb + xax; // ||y - X x||^2
     }
-    double ssr = yy - 2.0 * xb + xax; // ||y - X x||^2
     double n = (double)m.n, df = k + 1;
     double ll = 0.5 * (-n * (log(2 * M_PI) + 1 - log(n) + log(ssr)));
     *loglik = ll;
@@ -178,6 +217,7 @@ ABN_HDN void gauss_mle_fit(const DataMeta &m, const FitDesc &d, double *loglik, 
     if (coef)
         for (int i = 0; i < k; i++) coef[i] = x[i];
     if (se) se_from_information(A, k, ssr / (n - (double)k), se); // R/fitabn_mle.R:712-722
+    if (sse) *sse = ssr;
 }
 
 // ---- Bayes start values: beta0 = inv(X'X) X'y~ by LU, as generate_inits_n* do -------------------
@@ -218,7 +258,7 @@ ABN_HDN void bayes_inits(const DataMeta &m, const FitDesc &d, int child, FitStat
             xax += t * beta[i];
             xb += b[i] * beta[i];
         }
-        double rss = yy - 2.0 * xb + xax;
+        double rss = s.gaux ? gauss_aux_rss(*s.gaux, beta, (double)m.n) : yy - 2.0 * xb + xax;
         s.x0[k] = 1.0 / (rss / ((double)m.n - (double)k));
     }
 }
@@ -293,6 +333,7 @@ ABN_HD void state_setup(const DataMeta &m, const FitDesc &d, int child, const Co
     s.n = (double)m.n;
     s.lfact = m.node_lfact[child];
     s.icpt = (d.k > 0 && d.cols[0] < 0) ? 1 : 0;
+    s.gaux = nullptr;
 }
 
 // Coefficient slots of a row of ResultPtrs::coef (abn_result.coef): slot 0 = intercept, slot 1 + t = the t-th

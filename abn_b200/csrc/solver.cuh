@@ -349,6 +349,27 @@ enum Phase : int {
     PH_HYB_SET, PH_HYB_TRIAL, PH_HYB_JAC, PH_FINAL
 };
 
+// Centred moments of one Gaussian child's design [1 | x_1 .. x_k1] (plan.cuh gauss_centered_block): with them
+// ||y - X b||^2 = [Cyy - 2 b_s'Cxy + b_s'Cxx b_s] + n (ybar - b_0 - b_s'xbar)^2, free of the cancellation the raw
+// form y'y - 2 b'X'y + b'X'X b suffers when |mean(y)| >> sd(y) (the reference sums the residuals themselves,
+// src/irls_gaussian_fast.cpp:38-39).
+struct GaussAux {
+    int k1;
+    double Cxx[MAXM * MAXM], Cxy[MAXM], xbar[MAXM], Cyy, ybar;
+};
+
+ABN_HD double gauss_aux_rss(const GaussAux &g, const double *x, double n)
+{
+    double q = g.Cyy, c = g.ybar - x[0];
+    for (int i = 0; i < g.k1; i++) {
+        double t = 0.0;
+        for (int j = 0; j < g.k1; j++) t += A_(g.Cxx, i, j) * x[1 + j];
+        q += x[1 + i] * (t - 2.0 * g.Cxy[i]);
+        c -= x[1 + i] * g.xbar[i];
+    }
+    return q + n * c * c;
+}
+
 struct FitState {
     // problem
     int family, k, M; // k: design columns (H is k x k); M: unknowns
@@ -374,6 +395,7 @@ struct FitState {
     double J[MAXM * MAXM], Q[MAXM * MAXM], R[MAXM * MAXM];
     double fnorm, delta;
     int hy_iter, ncfail, ncsuc, nslow1, nslow2, scale, attempt, loop_iter;
+    const GaussAux *gaux; // Gaussian child with centred moments available (else null: raw Gram entries)
 };
 
 // ---- Bayes: raw sums -> grad g / hess g / g --------------------------------------------------
@@ -424,7 +446,7 @@ ABN_HD void gaus_eval(const FitState &s, const Control &c, const double *x, cons
         yxb += a.g[i] * x[i];
         xbxb += t * x[i];
     }
-    const double rss = -2.0 * yxb + xbxb + a.ll;
+    const double rss = s.gaux ? gauss_aux_rss(*s.gaux, x, n) : -2.0 * yxb + xbxb + a.ll;
     if (f) {
         for (int i = 0; i < m; i++)
             f[i] = (-1.0 / n) * (-(x[i] - c.prior_mean) / sd2 + tau * (a.g[i] - xtxb[i]));

@@ -29,6 +29,11 @@ struct DataMeta {
     const unsigned char *Xq;
     long long ldq;
     const int *col_card;
+    // centred second moments for Gaussian children (plan.cuh gauss_centered): Gc = Zc'Zc over
+    // Zc = [1 | X - col_mean], (1 + n_cols)^2 row-major, col_mean[j] = column mean as the raw Gram gives it.
+    // Residual sums of squares formed from these do not cancel when |mean| >> sd. Null: raw moments are used.
+    const double *Gc;
+    const double *col_mean;
 };
 
 struct ResultPtrs {

@@ -174,10 +174,11 @@ fit_wide_kernel(const DataMeta m, const Control c, const int *__restrict__ child
                 if (c.method == MLE) {
                     double ll, aic, bic;
                     int status;
-                    gauss_mle_fit(m, d, &ll, &aic, &bic, &status, S.st.x, out.se ? S.st.dir : nullptr);
+                    double sse;
+                    gauss_mle_fit(m, d, &ll, &aic, &bic, &status, S.st.x, out.se ? S.st.dir : nullptr, &sse);
                     write_coef(out, row, d, S.st.x, d.k);
                     if (out.se) { ResultPtrs o = out; o.coef = out.se; write_coef(o, row, d, S.st.dir, d.k); }
-                    if (out.sse) out.sse[row] = sse_of(m, d, S.st.x);
+                    if (out.sse) out.sse[row] = sse;
                     if (out.mlik) out.mlik[row] = ll;
                     if (out.aic) out.aic[row] = aic;
                     if (out.bic) out.bic[row] = bic;

@@ -143,7 +143,22 @@ def prepare(data_df, data_dists: dict, method: str, centre: bool = True) -> Prep
                 else:
                     x = _refactor(c)[0].astype(np.float64)  # as.numeric(factor(x)) - 1, _mle.R:410
             else:
-                x = np.asarray(c.values, dtype=np.float64)
+                v = np.asarray(c.values)
+                if method == "mle" and v.dtype.kind in "iu":
+                    # not class "numeric" in R: as.numeric(factor(x)) - 1, _mle.R:408-410 (codes 1/2 or -1/1 become 0/1)
+                    x = _refactor(c)[0].astype(np.float64)
+                else:
+                    x = v.astype(np.float64)
+            # check.valid.data (R/abn-internal.R:277-290): binary with both cases observed; a numeric column must
+            # already be coded 0/1 - anything else would be scored silently with y outside {0, 1}
+            uniq = np.unique(x)
+            if len(uniq) < 2:
+                raise ValueError(f"{c.name} is invalid as it must be binary with both cases being observed.")
+            if len(uniq) > 2:
+                raise ValueError(f"{c.name} is invalid as it must be binary. Multi-category variables should be split "
+                                 "into separate binary variables or defined as multinomial distributed.")
+            if not np.array_equal(uniq, [0.0, 1.0]):
+                raise ValueError(f"{c.name} is invalid - a numeric binomial column must be coded 0/1 (or be a factor)")
             blk, nm = x[:, None], [c.name]
         elif dist == "poisson":
             blk, nm = np.asarray(c.values, dtype=np.float64)[:, None], [c.name]

@@ -171,6 +171,18 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
     }
     DataMeta m{n, n, ds->n_nodes, ds->n_cols, D, ds->X, G.data(), ds->node_family, ds->node_col0, lfact.data(),
                gw_index.data(), n_pois, pois_node.data()};
+    // centred second moments for the Gaussian children, as abn_b200_data_create builds them (types.cuh DataMeta::Gc)
+    const int Dc = 1 + ds->n_cols;
+    std::vector<double> shift(Dc, 0.0), Gc((size_t)Dc * Dc, 0.0);
+    for (int a = 1; a < Dc; a++) shift[a] = G[a] / (double)n;
+    for (int a = 0; a < Dc; a++)
+        for (int b = a; b < Dc; b++) {
+            double s = 0.0;
+            for (long long i = 0; i < n; i++) s += (zc[a][i] - shift[a]) * (zc[b][i] - shift[b]);
+            Gc[(size_t)a * Dc + b] = Gc[(size_t)b * Dc + a] = s;
+        }
+    if (!std::getenv("ABN_SIM_NO_GC")) m.Gc = Gc.data();
+    m.col_mean = shift.data() + 1;
     Control c{ctrl->method, ctrl->max_iters, ctrl->solver, ctrl->nvars, ctrl->tol, ctrl->epsabs,
               ctrl->prior_mean, ctrl->prior_sd, ctrl->gam_shape, ctrl->gam_scale, ctrl->flags};
 
@@ -199,15 +211,18 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             ll = s.loglik; aic = s.aic; bic = s.bic; status = s.status; passes = s.passes;
         } else if (c.method == MLE && d.family == GAUSSIAN) {
             double x[MAXM], se[MAXM];
-            gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x, rp.se ? se : nullptr);
+            double sse;
+            gauss_mle_fit(m, d, &ll, &aic, &bic, &status, x, rp.se ? se : nullptr, &sse);
             write_coef(rp, r, d, x, d.k);
             if (rp.se) { ResultPtrs o = rp; o.coef = rp.se; write_coef(o, r, d, se, d.k); }
-            if (rp.sse) rp.sse[r] = sse_of(m, d, x);
+            if (rp.sse) rp.sse[r] = sse;
             passes = 1;
         } else {
             FitState s;
             std::memset(&s, 0, sizeof(s));
             state_setup(m, d, child, c, s);
+            GaussAux aux;
+            if (d.family == GAUSSIAN && gauss_centered_block(m, d, aux)) s.gaux = &aux; // as gauss_kernel
             if (c.method == BAYES) bayes_inits(m, d, child, s);
             PassAcc a;
             int mode = fit_begin(s, c);

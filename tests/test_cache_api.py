@@ -65,3 +65,22 @@ def test_dry_run_returns_node_definitions_without_a_gpu():
 def test_formula_parser():
     m = abncache._parse_formula("~a|b:c+d|.", ["a", "b", "c", "d"])
     assert m.tolist() == [[0, 1, 1, 0], [0, 0, 0, 0], [0, 0, 0, 0], [1, 1, 1, 0]]
+
+
+def test_binomial_columns_are_validated_and_recoded_like_the_reference():
+    """R/build_score_cache_mle.R:408-410 (anything not of class "numeric" is recoded through factor()) and
+    check.valid.data (R/abn-internal.R:277-290): binary, both cases observed."""
+    import numpy as np
+    import pytest
+    from abn_b200 import prep
+    rng = np.random.default_rng(0)
+    g = rng.standard_normal(40)
+    ones_twos = rng.integers(1, 3, 40)                       # integer column coded 1/2
+    P = prep.prepare({"b": ones_twos, "g": g}, {"b": "binomial", "g": "gaussian"}, "mle")
+    assert set(np.unique(P.X[:, 0])) == {0.0, 1.0} and np.array_equal(P.X[:, 0], ones_twos - 1.0)
+    with pytest.raises(ValueError, match="coded 0/1"):
+        prep.prepare({"b": ones_twos.astype(float), "g": g}, {"b": "binomial", "g": "gaussian"}, "mle")
+    with pytest.raises(ValueError, match="must be binary"):
+        prep.prepare({"b": rng.integers(0, 3, 40), "g": g}, {"b": "binomial", "g": "gaussian"}, "mle")
+    with pytest.raises(ValueError, match="both cases"):
+        prep.prepare({"b": np.zeros(40), "g": g}, {"b": "binomial", "g": "gaussian"}, "bayes")
