@@ -712,10 +712,116 @@ __device__ __forceinline__ void lean_stream(const double *const (&cp)[MAXK], lon
     }
 }
 
+// ---- the same tiles moved by the TMA unit ------------------------------------------------------------------
+// ABN_LEAN_TMA = 1: instead of 2 KD cp.async per lane and tile, lane 0 of the warp issues KD bulk copies
+// (cp.async.bulk, 1 KB each: the 128 rows of one column) that complete on the warp's own mbarrier, and every lane
+// waits on that barrier's phase. The copies do not pass through the load-store unit at all: no address
+// arithmetic in the other 31 lanes and - what matters for the narrow Poisson designs - no shared-memory store
+// wavefronts from the LSU, which together with the loads saturate the SM's 128 B/cycle shared-memory pipe before
+// the FP64 pipe (ncu, round 2). Same tile layout, same row order, same bits.
+#ifndef ABN_LEAN_TMA
+#define ABN_LEAN_TMA 0
+#endif
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double *smem_dst, const double *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// per-warp pipeline state that outlives a pass: the barriers (shared memory) and their phase bits
+struct TmaPipe {
+    unsigned long long *bar; // LEAN_STAGES barriers of this warp
+    unsigned phase;          // bit s = parity the next wait on stage s expects
+};
+
+template <int KD, typename RowFn>
+__device__ __forceinline__ void lean_stream_tma(const double *const (&cp)[MAXK], long long n, double *tile, TmaPipe &pipe,
+                                                RowTrack &tk, RowFn &&row)
+{
+    constexpr int TR = LEAN_TROWS, ST = LEAN_STAGES;
+    constexpr int KDA = KD > 0 ? KD : 1;
+    const int lane = threadIdx.x & 31;
+    const int ntiles = (KD > 0) ? (int)(n / TR) : 0;
+    auto issue = [&](int stage, int t) { // lane 0 only
+        double *dst = tile + stage * (KD * TR);
+        mbar_expect_tx(pipe.bar + stage, KD * TR * (unsigned)sizeof(double));
+#pragma unroll
+        for (int j = 0; j < KD; j++) bulk_g2s(dst + j * TR, cp[j] + (long long)t * TR, TR * (unsigned)sizeof(double), pipe.bar + stage);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < ST - 1; s++)
+            if (s < ntiles) issue(s, s);
+    }
+    int stage = 0, fill = ST - 1;
+    for (int it = 0; it < ntiles; it++) {
+        // the stage refilled here was read one iteration ago and its values have been consumed since
+        __syncwarp();
+        if (lane == 0 && it + ST - 1 < ntiles) issue(fill, it + ST - 1);
+        mbar_wait(pipe.bar + stage, (pipe.phase >> stage) & 1u);
+        pipe.phase ^= 1u << stage;
+        const double *t = tile + stage * (KD * TR) + 2 * lane;
+        double x[4][KDA];
+#pragma unroll
+        for (int j = 0; j < KD; j++) {
+            const double2 a = *reinterpret_cast<const double2 *>(t + j * TR);
+            const double2 b = *reinterpret_cast<const double2 *>(t + j * TR + 64);
+            x[0][j] = a.x; x[1][j] = a.y; x[2][j] = b.x; x[3][j] = b.y;
+        }
+        const int h0 = row(x[0]), h1 = row(x[1]), h2 = row(x[2]), h3 = row(x[3]);
+        tk.smax = max(max(tk.smax, h0), h1);
+        tk.umax = max(max(tk.umax, (unsigned)h0), (unsigned)h1);
+        tk.smax = max(max(tk.smax, h2), h3);
+        tk.umax = max(max(tk.umax, (unsigned)h2), (unsigned)h3);
+        fill = stage;
+        stage = (stage + 1 == ST) ? 0 : stage + 1;
+    }
+    __syncwarp();
+    for (long long i = (long long)ntiles * TR + lane; i < n; i += 32) {
+        double xt[KDA];
+#pragma unroll
+        for (int j = 0; j < KD; j++) xt[j] = __ldg(cp[j] + i);
+        const int h = row(xt);
+        tk.smax = max(tk.smax, h);
+        tk.umax = max(tk.umax, (unsigned)h);
+    }
+}
+
+template <int KD, typename RowFn>
+__device__ __forceinline__ void lean_rows(const double *const (&cp)[MAXK], long long n, double *tile, TmaPipe &pipe,
+                                          RowTrack &tk, RowFn &&row)
+{
+#if ABN_LEAN_TMA
+    lean_stream_tma<KD>(cp, n, tile, pipe, tk, row);
+#else
+    (void)pipe;
+    lean_stream<KD>(cp, n, tile, tk, row);
+#endif
+}
+
 // Poisson with an intercept (see warp_pass_pois for the identities). false: eta left (-700, 700), nothing written.
 template <int K, int MODE>
 __device__ __forceinline__ bool lean_pass_pois(const double *const (&cp)[MAXK], const double *beta_sm, const double *xty,
-                                               long long n, const double *tab256, PassAcc *acc_sm, double *tile)
+                                               long long n, const double *tab256, PassAcc *acc_sm, double *tile, TmaPipe &pipe)
 {
     constexpr int KD = K - 1;
     constexpr int KDA = KD > 0 ? KD : 1;
@@ -751,7 +857,7 @@ __device__ __forceinline__ bool lean_pass_pois(const double *const (&cp)[MAXK], 
         }
         return hi_word(eta);
     };
-    lean_stream<KD>(cp, n, tile, tk, row);
+    lean_rows<KD>(cp, n, tile, pipe, tk, row);
     if (__any_sync(0xffffffffu, (tk.smax >= 0x4085E000) | (tk.umax >= 0xC085E000u))) return false; // |eta| >= 700, NaN
 #pragma unroll
     for (int j = 0; j < NH; j++) H[j] = warp_sum(H[j]);
@@ -784,7 +890,7 @@ __device__ __forceinline__ bool lean_pass_pois(const double *const (&cp)[MAXK], 
 template <int KIND, int K, int MODE>
 __device__ __forceinline__ bool lean_pass_bin(const double *const (&cp)[MAXK], const double *beta_sm, const double *xty,
                                               const double *xt1, long long n, const RowConst rc, const double *tab256,
-                                              PassAcc *acc_sm, double *tile)
+                                              PassAcc *acc_sm, double *tile, TmaPipe &pipe)
 {
     constexpr int KD = K - 1;
     constexpr int KDA = KD > 0 ? KD : 1;
@@ -833,7 +939,7 @@ __device__ __forceinline__ bool lean_pass_bin(const double *const (&cp)[MAXK], c
         }
         return hi_word(eta);
     };
-    lean_stream<KD>(cp, n, tile, tk, row);
+    lean_rows<KD>(cp, n, tile, pipe, tk, row);
     const int out_of_range = MLE_ ? ((tk.smax >= 0x40280000) | (tk.umax >= 0xC0762E42u))
                                   : ((tk.smax >= 0x4085E000) | (tk.umax >= 0xC085E000u));
     if (__any_sync(0xffffffffu, out_of_range)) return false;
@@ -875,13 +981,13 @@ __device__ __forceinline__ bool lean_pass_bin(const double *const (&cp)[MAXK], c
 template <int KIND, int K, bool ICPT, int MODE>
 __device__ __forceinline__ void run_pass(const double *__restrict__ y, const double *const (&cp)[MAXK],
                                          const double *beta_sm, long long n, const RowConst rc, PassAcc *acc_sm,
-                                         double *tile, const double *xty, const double *tab256, int &careful)
+                                         double *tile, const double *xty, const double *tab256, int &careful, TmaPipe &pipe)
 {
 #if ABN_LEAN
     if (ICPT && !careful && KIND != RK_PINIT) {
         bool ok;
-        if (KIND == RK_POIS) ok = lean_pass_pois<K, MODE>(cp, beta_sm, xty, n, tab256, acc_sm, tile);
-        else ok = lean_pass_bin<KIND == RK_BIN_MLE ? RK_BIN_MLE : RK_BIN_BAYES, K, MODE>(cp, beta_sm, xty, xty + MAXK, n, rc, tab256, acc_sm, tile);
+        if (KIND == RK_POIS) ok = lean_pass_pois<K, MODE>(cp, beta_sm, xty, n, tab256, acc_sm, tile, pipe);
+        else ok = lean_pass_bin<KIND == RK_BIN_MLE ? RK_BIN_MLE : RK_BIN_BAYES, K, MODE>(cp, beta_sm, xty, xty + MAXK, n, rc, tab256, acc_sm, tile, pipe);
         if (ok) return;
         careful = 1; // this fit leaves the range of the lean row ops: careful passes from here on
     }
@@ -936,6 +1042,15 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
     PassAcc *acc = &acc_all[warp];
     double *tile = stage_tiles + (size_t)warp * fit_stage_doubles_per_warp<K, ICPT>();
     double *xty = xty_all[warp];
+    __shared__ unsigned long long tma_bars[FIT_WARPS][LEAN_STAGES];
+    TmaPipe pipe{tma_bars[warp], 0u};
+#if ABN_LEAN_TMA
+    if (lane == 0) {
+        for (int s = 0; s < LEAN_STAGES; s++) mbar_init(pipe.bar + s, 1u);
+        mbar_fence_init();
+    }
+    __syncwarp();
+#endif
     const double *lean_tab = exp256_tab + (ABN_EXP_REPLICATED ? (lane & (ABN_EXP64R_COPIES - 1)) : 0);
 
     for (;;) {
@@ -988,12 +1103,12 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
             // passes by mode, per bucket: the numerator of the FP64 roofline (abn_timing.kernel_fp64)
             if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(counter + 2) + mode, 1ull);
             // only the modes a row kind's state machines can ask for are instantiated
-            if (mode == PASS_HG) run_pass<KIND, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
-            else if (mode == PASS_FULL) run_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
-            else if (mode == PASS_LL) run_pass<KIND, K, ICPT, PASS_LL>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
-            else if (KIND != RK_BIN_MLE && mode == PASS_GRAD) run_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
-            else if (KIND != RK_BIN_MLE && mode == PASS_HESS) run_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
-            else if (KIND == RK_POIS && mode == PASS_PINIT) run_pass<RK_PINIT, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful);
+            if (mode == PASS_HG) run_pass<KIND, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful, pipe);
+            else if (mode == PASS_FULL) run_pass<KIND, K, ICPT, PASS_FULL>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful, pipe);
+            else if (mode == PASS_LL) run_pass<KIND, K, ICPT, PASS_LL>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful, pipe);
+            else if (KIND != RK_BIN_MLE && mode == PASS_GRAD) run_pass<KIND, K, ICPT, PASS_GRAD>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful, pipe);
+            else if (KIND != RK_BIN_MLE && mode == PASS_HESS) run_pass<KIND, K, ICPT, PASS_HESS>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful, pipe);
+            else if (KIND == RK_POIS && mode == PASS_PINIT) run_pass<RK_PINIT, K, ICPT, PASS_HG>(y, cp, st.x, m.n, rc, acc, tile, xty, lean_tab, careful, pipe);
             __syncwarp();
             if (lane == 0) mode = fit_consume(st, c, *acc);
             mode = __shfl_sync(0xffffffffu, mode, 0);

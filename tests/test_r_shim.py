@@ -68,8 +68,8 @@ def _call(L, name, args):
     return out
 
 
-def _list(L, s):
-    s = s.contents
+def _list(L, sx):
+    s = sx.contents
     assert s.type == VECSXP
     elts = C.cast(s.data, C.POINTER(SEXP))
     out = {}
@@ -79,7 +79,8 @@ def _list(L, s):
         arr = np.ctypeslib.as_array(buf, shape=(e.length,)).copy()
         if e.nrow:
             arr = arr.reshape((e.ncol, e.nrow)).T  # column-major
-        out[L.stub_name(elts[i] and C.cast(C.pointer(s), SEXP), i).decode() or i] = arr
+        name = s.names[i].decode() if s.names else ""
+        out[name or i] = arr
     return out
 
 
