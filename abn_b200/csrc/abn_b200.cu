@@ -27,6 +27,7 @@ cudaError_t abn_wide_launch(const abnc::DataMeta &m, const abnc::Control &c, con
                             int width, const int *list, int count, int *counter, abnc::ResultPtrs out, int sm_count,
                             cudaStream_t stream);
 int abn_wide_max_k();
+int abn_cell_ovf_slots(int sm_count); // fit_cell.cu: warps of all contingency-table kernels that may run together
 // fit_cell.cu: all-discrete designs on contingency tables (kind: RK_BIN_MLE, RK_POIS, RK_BIN_BAYES)
 cudaError_t abn_cell_launch(int kind, int large, const abnc::DataMeta &m, const abnc::Control &c, const abn::FitDesc *descs,
                             const int *child, const int *list, int count, int *counter, abnc::ResultPtrs out,
@@ -36,8 +37,8 @@ cudaError_t abn_cell_launch(int kind, int large, const abnc::DataMeta &m, const 
 constexpr int BUCKET_SLOT_INTS = 16;
 
 // FP64 instructions one observation row costs in a pass of the streaming kernels, by row kind, design width and pass
-// mode - counted from the SASS of the lean passes (profiles/sass_r2_*; e.g. Poisson K = 4: 3 eta + 10 exp + 13 H = 26,
-// binomial K = 4 HG: 3 + 10 + 1 + 3 rcp + 1 w + 13 H + 4 S = 35). The rare careful / no-intercept passes are
+// mode - counted from the SASS of the lean passes (profiles/sass_r2_*; e.g. Poisson K = 4: 3 eta + 9 exp + 13 H = 25,
+// binomial K = 4 HG: 3 + 9 + 1 + 3 rcp + 1 w + 13 H + 4 S = 34). The rare careful / no-intercept passes are
 // counted with the same formula.
 static int fp64_per_row(int fam /*0 binomial, 1 Poisson*/, int k, int mode)
 {
@@ -46,7 +47,7 @@ static int fp64_per_row(int fam /*0 binomial, 1 Poisson*/, int k, int mode)
     const bool need_l = (mode == PASS_FULL || mode == PASS_LL);
     const int kd = k > 0 ? k - 1 : 0;
     const int hsum = 1 + 2 * kd + k * kd / 2; // w; w x_q; (w x_p); (w x_p) x_q
-    int c = kd + 10;                          // eta, exp (fast_exp64r)
+    int c = kd + 9 + (ABN_EXP_REPLICATED ? 1 : 0); // eta, exp
     if (fam == 1) return c + (need_h ? hsum : (need_g ? 1 + kd : 1));
     c += 1;                                   // d = 1 + e
     if (need_l) c += 13;                      // log(1 + e) and its sum
@@ -298,6 +299,38 @@ discretize_kernel(const double *__restrict__ X, long long ld, long long n, unsig
     }
 }
 
+// col_tail[c * 8 + b] = rows of column c whose byte code is >= 2^b: what capping the column at b bits would send
+// to the overflow lists (fit_cell.cuh cell_bits_of)
+__global__ void __launch_bounds__(256)
+col_tail_kernel(const unsigned char *__restrict__ Xq, long long ldq, long long n, unsigned *__restrict__ col_tail)
+{
+    __shared__ unsigned acc[8];
+    if (threadIdx.x < 8) acc[threadIdx.x] = 0u;
+    __syncthreads();
+    const int col = blockIdx.y;
+    const long long r0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    unsigned cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (r0 < n) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(Xq + (long long)col * ldq + r0);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (r0 + i >= n) break;
+            const unsigned code = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+#pragma unroll
+            for (int b = 0; b < 8; b++) cnt[b] += (code >= (1u << b)) ? 1u : 0u;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        unsigned s = cnt[b];
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&acc[b], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && acc[threadIdx.x]) atomicAdd(&col_tail[col * 8 + threadIdx.x], acc[threadIdx.x]);
+}
+
 __global__ void col_card_kernel(int n_cols, const int *__restrict__ col_bad, const int *__restrict__ col_max, int *__restrict__ col_card)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,6 +430,7 @@ struct abn_data {
     int *dFamily = nullptr, *dCol0 = nullptr, *dGwIndex = nullptr, *dPoisNode = nullptr;
     unsigned char *dXq = nullptr; // byte codes of the discrete columns (fit_cell.cuh)
     int *dColCard = nullptr;
+    unsigned *dColTail = nullptr, *dCellOvf = nullptr; // capped codes: tail counts, overflow lists
     double *dGc = nullptr, *dColMean = nullptr; // centred Gram and the shifts it was built with ([0] = 0)
     std::vector<int> family, col0, gw_index;
     int sm_count = 148;
@@ -435,6 +469,7 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
     dev_free(d->dX, d->stream); dev_free(d->dG, d->stream); dev_free(d->dLfact, d->stream); dev_free(d->dFamily, d->stream); dev_free(d->dCol0, d->stream);
     dev_free(d->dGwIndex, d->stream); dev_free(d->dPoisNode, d->stream);
     dev_free(d->dXq, d->stream); dev_free(d->dColCard, d->stream);
+    dev_free(d->dColTail, d->stream); dev_free(d->dCellOvf, d->stream);
     dev_free(d->dGc, d->stream); dev_free(d->dColMean, d->stream);
     dev_free(d->dBucketStart, d->stream); dev_free(d->dCounters, d->stream);
     cudaStreamSynchronize(d->stream); // the frees above are stream-ordered
@@ -575,6 +610,16 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     if (use_cells) {
         TRY_OR_FREE(dev_alloc(&d->dXq, (size_t)ld * ds->n_cols, d->stream));
         TRY_OR_FREE(dev_alloc(&d->dColCard, (size_t)ds->n_cols * 3 * sizeof(int), d->stream)); // card | bad | max
+        TRY_OR_FREE(dev_alloc(&d->dColTail, (size_t)ds->n_cols * 8 * sizeof(unsigned), d->stream));
+        // overflow lists of the capped contingency tables: n / 8 rows per resident warp (3.5 GB for n = 1e6 on 148 SMs);
+        // skipped - and with it the capping - when that would exceed 8 GB or no column can need it
+        bool any_count = false;
+        for (int i = 0; i < ds->n_nodes; i++) any_count |= ds->node_family[i] == ABN_POISSON;
+        const size_t stride = (size_t)ds->n / 8 + 64;
+        const size_t ovf_bytes = (size_t)abn_cell_ovf_slots(d->sm_count) * stride * sizeof(unsigned);
+        const char *no_cap = std::getenv("ABN_B200_NO_CELL_CAPS");
+        if (any_count && ovf_bytes <= (8ull << 30) && !(no_cap && *no_cap && *no_cap != '0'))
+            TRY_OR_FREE(dev_alloc(&d->dCellOvf, ovf_bytes, d->stream));
     }
     tr.mark("create: streams + cudaMalloc");
     TRY_OR_FREE(cudaMemsetAsync(d->dX, 0, (size_t)ld * ds->n_cols * sizeof(double), d->stream));
@@ -603,6 +648,9 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     d->m.Xq = nullptr;
     d->m.ldq = ld;
     d->m.col_card = nullptr;
+    d->m.col_tail = nullptr;
+    d->m.cell_ovf = nullptr;
+    d->m.cell_ovf_stride = 0;
     d->m.Gc = nullptr;
     d->m.col_mean = nullptr;
     if (d->dXq) {
@@ -612,16 +660,21 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
             const long long groups = (ds->n + 15) / 16;
             discretize_kernel<<<dim3((unsigned)((groups + 255) / 256), ds->n_cols), 256, 0, d->stream>>>(d->dX, ld, ds->n, d->dXq, ld, bad, mx);
             col_card_kernel<<<(ds->n_cols + 127) / 128, 128, 0, d->stream>>>(ds->n_cols, bad, mx, d->dColCard);
-            e = cudaGetLastError();
+            e = cudaMemsetAsync(d->dColTail, 0, (size_t)ds->n_cols * 8 * sizeof(unsigned), d->stream);
+            col_tail_kernel<<<dim3((unsigned)((groups + 255) / 256), ds->n_cols), 256, 0, d->stream>>>(d->dXq, ld, ds->n, d->dColTail);
+            if (e == cudaSuccess) e = cudaGetLastError();
         }
         if (e != cudaSuccess) {
             rc = fail(err, errlen, ABN_ERR_CUDA, "discretize: %s", cudaGetErrorString(e));
             abn_b200_data_destroy(d);
             return rc;
         }
-        d->timing.launches += 2;
+        d->timing.launches += 3;
         d->m.Xq = d->dXq;
         d->m.col_card = d->dColCard;
+        d->m.col_tail = d->dColTail;
+        d->m.cell_ovf = d->dCellOvf;
+        d->m.cell_ovf_stride = (long long)(ds->n / 8 + 64);
     }
     rc = compute_gram(d, err, errlen);
     if (rc != ABN_OK) { abn_b200_data_destroy(d); return rc; }

@@ -38,11 +38,21 @@ constexpr int CELL_SMALL_BITS = 6;
 constexpr int CELL_MAX_BITS = 10;         // widest cell index taken: at least 4 replicas per counter (<= 8 phases)
 constexpr int CELL_WARPS = 4;             // warps per CTA
 
-// bits needed for codes 0 .. card-1
-ABN_HD int bits_for(int card)
+// Bits the codes of a column get in the cell index. A count column whose codes would need more than 3 bits is
+// CAPPED where the data allow it: codes below 2^b are binned, the rows at or beyond it - at most 1/32 of the
+// data per column, known from the column's tail counts - are kept as an explicit overflow list and summed row by
+// row in every pass. A Poisson parent with counts up to 40 then costs 3..4 bits instead of 6, which brings
+// designs with two or three count parents into the table sizes this kernel is good at.
+ABN_HD int cell_bits_of(const DataMeta &m, int col, bool *capped)
 {
-    int b = 1;
-    while ((1 << b) < card) b++;
+    const int card = m.col_card[col];
+    int full = 1;
+    while ((1 << full) < card) full++;
+    *capped = false;
+    if (full <= 3 || m.col_tail == nullptr || m.cell_ovf == nullptr) return full;
+    int b = 3;
+    while (b < full && (long long)m.col_tail[col * 8 + b] * 32 > m.n) b++;
+    *capped = b < full;
     return b;
 }
 
@@ -54,13 +64,16 @@ ABN_HD int cell_eligible(const DataMeta &m, const FitDesc &d, int method, int fl
     if (d.family != BINOMIAL && d.family != POISSON) return 0;
     if (d.family == POISSON && method == MLE && (flags & 1)) return 0; // the reference's start-value pass needs y per row
     int bits = (d.family == BINOMIAL) ? 1 : 0;                             // the response is part of a binomial cell
+    int ncapped = 0;
     for (int j = 0; j < d.k; j++) {
         if (d.cols[j] < 0) continue;
-        const int card = m.col_card[d.cols[j]];
-        if (card <= 0) return 0;
-        bits += bits_for(card);
+        if (m.col_card[d.cols[j]] <= 0) return 0;
+        bool capped;
+        bits += cell_bits_of(m, d.cols[j], &capped);
+        ncapped += capped;
     }
     if (d.family == BINOMIAL && m.col_card[d.ycol] != 2) return 0;
+    if (ncapped > 4) return 0; // the overflow list holds n / 8 rows: 4 columns x n / 32
     return bits <= CELL_SMALL_BITS ? 1 : (bits <= CELL_MAX_BITS ? 2 : 0);
 }
 
@@ -71,6 +84,9 @@ struct CellPlan {
     int bits[MAXK + 1];
     int total_bits;
     int xslot[MAXK];     // design column j takes its value from byte column xslot[j] (-1: intercept)
+    int cap[MAXK + 1];   // codes >= cap go to the overflow list (256: the column is not capped)
+    int any_cap;
+    unsigned n_ovf;      // rows in the overflow list of the fit in flight
 };
 
 // Contingency table of the fit. Counter of cell c: tab[(c << lc) | (set << lcl) | (lane mod copies)], copies = 2^lcl
@@ -82,14 +98,21 @@ struct CellPlan {
 //   * a read-modify-write is a ~35-cycle dependent chain (LDS, add, STS) and two rows of a lane may meet the same
 //     counter, so the chain cannot be overlapped - unless consecutive rows go to different sets: with 4 sets the
 //     4 counters of a row group are distinct by construction and their loads, adds and stores are issued together.
+// Rows with a code at or beyond its column's cap are not counted: their indices go to `ovf` (ascending row order
+// within a lane step, lane by lane - a fixed order) and `*n_ovf` returns how many.
 template <int NC>
-__device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPlan &cp, unsigned *tab, int cap, int lcl, int lc)
+__device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPlan &cp, unsigned *tab, int cap, int lcl, int lc,
+                                                unsigned *ovf, unsigned *n_ovf)
 {
     const int lane = threadIdx.x & 31;
     const unsigned char *colp[NC];
     int sh[NC];
+    unsigned capv[NC];
 #pragma unroll
-    for (int j = 0; j < NC; j++) { colp[j] = m.Xq + (long long)cp.col[j] * m.ldq; sh[j] = cp.shift[j]; }
+    for (int j = 0; j < NC; j++) { colp[j] = m.Xq + (long long)cp.col[j] * m.ldq; sh[j] = cp.shift[j]; capv[j] = (unsigned)cp.cap[j]; }
+    const bool any_cap = cp.any_cap != 0;
+    unsigned novf = 0;
+    const unsigned lane_lt = (1u << lane) - 1u;
     unsigned *const mine = tab + (lane & ((1 << lcl) - 1));
     const int nphase = 32 >> lcl, my_phase = lane >> lcl;
     const int nsets = 1 << (lc - lcl); // 1, 2 or 4 (only with 32 lane replicas)
@@ -98,7 +121,7 @@ __device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPla
     const long long steps = (n16 + 31) / 32; // every lane runs the same number of steps (the phases synchronise)
     // 16 rows per lane and step: one 16-byte load per column; the codes of 4 rows are combined at once when
     // the whole index fits a byte (<= 256 cells), otherwise row by row
-    const bool bytewise = cp.total_bits <= 8;
+    const bool bytewise = cp.total_bits <= 8 && !any_cap;
     for (long long st = 0; st < steps; st++) {
         const long long c = st * 32 + lane;
         const bool live = c < n16;
@@ -117,21 +140,50 @@ __device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPla
 #pragma unroll
                 for (int b = 0; b < 4; b++) cells[4 * q + b] = (w[q] >> (8 * b)) & 0xffu;
         } else {
+            unsigned over = 0; // bit r: row r of this lane's 16 goes to the overflow list
 #pragma unroll
             for (int q = 0; q < 4; q++) {
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
-                    unsigned cell = 0;
+                    unsigned cell = 0, o = 0;
 #pragma unroll
                     for (int j = 0; j < NC; j++) {
                         const unsigned word = q == 0 ? v[j].x : (q == 1 ? v[j].y : (q == 2 ? v[j].z : v[j].w));
-                        cell |= ((word >> (8 * b)) & 0xffu) << sh[j];
+                        const unsigned code = (word >> (8 * b)) & 0xffu;
+                        o |= (code >= capv[j]) ? 1u : 0u;
+                        cell |= code << sh[j];
                     }
                     cells[4 * q + b] = cell;
+                    over |= o << (4 * q + b);
+                }
+            }
+            if (any_cap) {
+                // a row beyond a cap is sent to the scratch counter and appended to the list: per row of the step one
+                // ballot gives every lane its slot (lanes in order, rows in order)
+                if (!live) over = 0;
+#pragma unroll
+                for (int r = 0; r < 16; r++) {
+                    const bool mine_over = (over >> r) & 1u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, mine_over);
+                    if (mine_over) {
+                        ovf[novf + __popc(bal & lane_lt)] = (unsigned)(c * 16 + r);
+                        cells[r] = 0xffffffffu;
+                    }
+                    novf += __popc(bal);
                 }
             }
         }
-        if (nphase == 1) {
+        if (any_cap) {
+            // counted rows only (an overflow row carries the marker); same phases as below
+            for (int ph = 0; ph < nphase; ph++) {
+                if (my_phase == ph && live) {
+#pragma unroll
+                    for (int r = 0; r < 16; r++)
+                        if (cells[r] != 0xffffffffu) { unsigned *p = mine + (cells[r] << lc); *p = *p + 1u; }
+                }
+                if (nphase > 1) __syncwarp();
+            }
+        } else if (nphase == 1) {
             if (live) {
                 if (nsets == 4) {
 #pragma unroll
@@ -169,22 +221,32 @@ __device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPla
         const long long i = i0 + lane;
         const bool live = i < m.n;
         unsigned cell = 0;
+        bool o = false;
         if (live) {
 #pragma unroll
-            for (int j = 0; j < NC; j++) cell |= (unsigned)__ldg(colp[j] + i) << sh[j];
+            for (int j = 0; j < NC; j++) {
+                const unsigned code = __ldg(colp[j] + i);
+                o |= code >= capv[j];
+                cell |= code << sh[j];
+            }
         }
-        unsigned *p = live ? mine + (cell << lc) : dead;
+        const unsigned bal = __ballot_sync(0xffffffffu, o);
+        if (o) ovf[novf + __popc(bal & lane_lt)] = (unsigned)i;
+        novf += __popc(bal);
+        unsigned *p = (live && !o) ? mine + (cell << lc) : dead;
         for (int ph = 0; ph < nphase; ph++) {
             if (my_phase == ph) *p = *p + 1u;
             __syncwarp();
         }
     }
+    *n_ovf = novf;
 }
 
 // one "data pass" over the cells. acc gets the same sums a row pass would produce.
 template <int KIND>
-__device__ __forceinline__ void cell_pass(const CellPlan &cp, const unsigned *cnt, int k, const double *beta_sm,
-                                          const double *xty, int mode, const RowConst rc, PassAcc *acc_sm)
+__device__ __forceinline__ void cell_pass(const DataMeta &m, const CellPlan &cp, const unsigned *cnt, const unsigned *ovf,
+                                          int k, const double *beta_sm, const double *xty, int mode, const RowConst rc,
+                                          PassAcc *acc_sm)
 {
     const int lane = threadIdx.x & 31;
     const bool need_h = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_HESS);
@@ -197,28 +259,45 @@ __device__ __forceinline__ void cell_pass(const CellPlan &cp, const unsigned *cn
     for (int j = 0; j < NTRI; j++) H[j] = 0.0;
     RowTrack tk = row_track_init();
     const int ncell = 1 << cp.total_bits;
-    for (int c = lane; c < ncell; c += 32) {
-        const unsigned N = cnt[c];
-        if (N == 0) continue;
-        const double dn = (double)N;
-        double x[MAXK];
+    // the cells first, then the rows of the overflow list (codes beyond a cap), one "row" each with weight 1
+    const int nunit = ncell + (int)cp.n_ovf;
+    for (int u = lane; u < nunit; u += 32) {
+        double dn, x[MAXK], y = 0.0;
+        if (u < ncell) {
+            const unsigned N = cnt[u];
+            if (N == 0) continue;
+            dn = (double)N;
+#pragma unroll
+            for (int j = 0; j < MAXK; j++) {
+                x[j] = 0.0;
+                if (j < k) {
+                    const int s = cp.xslot[j];
+                    x[j] = s < 0 ? 1.0 : (double)((u >> cp.shift[s]) & ((1 << cp.bits[s]) - 1));
+                }
+            }
+            y = (double)(u & 1); // the response is the first bit field of a binomial cell
+        } else {
+            const long long row = ovf[u - ncell];
+            dn = 1.0;
+#pragma unroll
+            for (int j = 0; j < MAXK; j++) {
+                x[j] = 0.0;
+                if (j < k) {
+                    const int s = cp.xslot[j];
+                    x[j] = s < 0 ? 1.0 : (double)m.Xq[(long long)cp.col[s] * m.ldq + row];
+                }
+            }
+            if (KIND != RK_POIS) y = (double)m.Xq[(long long)cp.col[0] * m.ldq + row];
+        }
         double eta = 0.0;
 #pragma unroll
-        for (int j = 0; j < MAXK; j++) {
-            x[j] = 0.0;
-            if (j < k) {
-                const int s = cp.xslot[j];
-                x[j] = s < 0 ? 1.0 : (double)((c >> cp.shift[s]) & ((1 << cp.bits[s]) - 1));
-                eta = fma(x[j], beta[j], eta);
-            }
-        }
+        for (int j = 0; j < MAXK; j++) eta = fma(x[j], beta[j], eta);
         double w = 0.0, r = 0.0, l = 0.0;
         if (KIND == RK_POIS) {
             row_track(tk, eta);
             const double E = fast_exp(clamp_lo700(eta), rc.tab);
             w = E; r = E; l = E; // r, l: the parts that are summed per cell; X'y is added below
         } else {
-            const double y = (double)(c & 1); // the response is the first bit field of a binomial cell
             RowOp<KIND>::template apply<true, true, true>(eta, y, rc, w, r, l, tk, true);
         }
         w *= dn; r *= dn; l *= dn;
@@ -285,7 +364,7 @@ __device__ __forceinline__ void cell_pass(const CellPlan &cp, const unsigned *cn
 template <int KIND, int CAPBITS>
 __global__ void __launch_bounds__(CELL_WARPS * 32, CAPBITS == CELL_SMALL_CAPBITS ? 4 : 2)
 fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ child,
-                const int *__restrict__ list, int count, int *counter, ResultPtrs out)
+                const int *__restrict__ list, int count, int *counter, ResultPtrs out, int ovf_slot0)
 {
     __shared__ FitState st_all[CELL_WARPS];
     __shared__ PassAcc acc_all[CELL_WARPS];
@@ -304,6 +383,8 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
     CellPlan &cp = plan_all[warp];
     double *xty = xty_all[warp];
     unsigned *tab = cell_tabs + (size_t)warp * (CAP + 32);
+    // this warp's overflow list (row indices beyond a cap); `ovf_slot0` separates the kernels that may run together
+    unsigned *ovf = m.cell_ovf ? m.cell_ovf + ((long long)ovf_slot0 + (long long)blockIdx.x * CELL_WARPS + warp) * m.cell_ovf_stride : nullptr;
 
     for (;;) {
         int idx = 0;
@@ -317,15 +398,21 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
         if (lane == 0) {
             int nc = 0, sh = 0;
             if (d.family == BINOMIAL) { cp.col[0] = d.ycol; cp.shift[0] = 0; cp.bits[0] = 1; nc = 1; sh = 1; }
+            cp.cap[0] = 256;
+            cp.any_cap = 0;
             for (int j = 0; j < k; j++) {
                 if (d.cols[j] < 0) { cp.xslot[j] = -1; continue; }
-                const int b = bits_for(m.col_card[d.cols[j]]);
+                bool capped;
+                const int b = cell_bits_of(m, d.cols[j], &capped);
                 cp.col[nc] = d.cols[j]; cp.shift[nc] = sh; cp.bits[nc] = b;
+                cp.cap[nc] = capped ? (1 << b) : 256;
+                cp.any_cap |= capped ? 1 : 0;
                 cp.xslot[j] = nc;
                 nc++; sh += b;
             }
             cp.ncol = nc;
             cp.total_bits = sh;
+            cp.n_ovf = 0;
             const long long gy = gram_col(d.ycol);
             for (int j = 0; j < k; j++) xty[j] = m.G[(long long)gidx(d, j) * m.D + gy];
         }
@@ -335,19 +422,21 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
         const int lc = min(7, CAPBITS - tb);        // ... times the sets across rows (cell_count_rows)
         for (int i = lane; i < (1 << (tb + lc)); i += 32) tab[i] = 0u;
         __syncwarp();
+        unsigned novf = 0;
         switch (cp.ncol) {
         case 0: break;
-        case 1: cell_count_rows<1>(m, cp, tab, CAP, lcl, lc); break;
-        case 2: cell_count_rows<2>(m, cp, tab, CAP, lcl, lc); break;
-        case 3: cell_count_rows<3>(m, cp, tab, CAP, lcl, lc); break;
-        case 4: cell_count_rows<4>(m, cp, tab, CAP, lcl, lc); break;
-        case 5: cell_count_rows<5>(m, cp, tab, CAP, lcl, lc); break;
-        case 6: cell_count_rows<6>(m, cp, tab, CAP, lcl, lc); break;
-        case 7: cell_count_rows<7>(m, cp, tab, CAP, lcl, lc); break;
-        case 8: cell_count_rows<8>(m, cp, tab, CAP, lcl, lc); break;
-        default: cell_count_rows<MAXK + 1>(m, cp, tab, CAP, lcl, lc); break;
+        case 1: cell_count_rows<1>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+        case 2: cell_count_rows<2>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+        case 3: cell_count_rows<3>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+        case 4: cell_count_rows<4>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+        case 5: cell_count_rows<5>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+        case 6: cell_count_rows<6>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+        case 7: cell_count_rows<7>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+        case 8: cell_count_rows<8>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+        default: cell_count_rows<MAXK + 1>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
         }
         __syncwarp();
+        if (lane == 0) cp.n_ovf = novf;
         // fold the replicas: counter of cell c ends up at tab[c]. Round r handles cells 32 r .. 32 r + 31: all
         // reads of a round precede its writes, and later rounds read only beyond what has been written
         if (cp.ncol == 0) {
@@ -387,7 +476,7 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
         mode = __shfl_sync(0xffffffffu, mode, 0);
         __syncwarp();
         while (mode != PASS_DONE) {
-            cell_pass<KIND>(cp, tab, k, st.x, xty, mode, rc, acc);
+            cell_pass<KIND>(m, cp, tab, ovf, k, st.x, xty, mode, rc, acc);
             __syncwarp();
             if (lane == 0) mode = fit_consume(st, c, *acc);
             mode = __shfl_sync(0xffffffffu, mode, 0);

@@ -628,10 +628,12 @@ __device__ __forceinline__ void warp_pass_bin(const double *__restrict__ y, cons
 #define ABN_LEAN 1
 #endif
 constexpr int LEAN_STAGES = ABN_LEAN_STAGES;
-// exp of the lean row ops: 1 = 64-entry table in 16 bank-interleaved replicas (fast_exp64r, 10 FP64 + 2 shared-memory
-// wavefronts), 0 = 256-entry table (fast_exp256, 9 FP64 + ~9 wavefronts)
+// exp of the lean row ops: 0 = 256-entry table (fast_exp256, 9 FP64 instructions, a conflict-prone table read),
+// 1 = 64-entry table in 16 bank-interleaved replicas (fast_exp64r, conflict-free read, 10 FP64 instructions). The
+// replicas take the shared-memory pipe of the Poisson pass from 68 % to 58 % busy (ncu), but the extra FP64
+// instruction costs more than that buys
 #ifndef ABN_EXP_REPLICATED
-#define ABN_EXP_REPLICATED 1
+#define ABN_EXP_REPLICATED 0 // measured on one box (profiles/ab_r2_variants.txt): 206.6 k fits/s replicated, 216.8 k with 256 entries
 #endif
 #if ABN_EXP_REPLICATED
 #define ABN_LEAN_EXP fast_exp64r

@@ -29,6 +29,11 @@ struct DataMeta {
     const unsigned char *Xq;
     long long ldq;
     const int *col_card;
+    // capped codes: col_tail[c * 8 + b] = rows of column c whose code is >= 2^b (b = 0..7); rows beyond a cap go
+    // to the warp's overflow list cell_ovf + slot * cell_ovf_stride (row indices). Null: no capping.
+    const unsigned *col_tail;
+    unsigned *cell_ovf;
+    long long cell_ovf_stride;
     // centred second moments for Gaussian children (plan.cuh gauss_centered): Gc = Zc'Zc over
     // Zc = [1 | X - col_mean], (1 + n_cols)^2 row-major, col_mean[j] = column mean as the raw Gram gives it.
     // Residual sums of squares formed from these do not cancel when |mean| >> sd. Null: raw moments are used.

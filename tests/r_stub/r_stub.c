@@ -49,7 +49,14 @@ SEXP mkNamed(int type, const char **names)
     int n = 0;
     while (names[n][0]) n++;
     SEXP s = make(type, n, NULL);
-    s->names = names;
+    /* R copies the names into a STRSXP; the caller's array may live on its stack */
+    const char **copy = (const char **)keep(calloc((size_t)n + 1, sizeof(char *)));
+    for (int i = 0; i < n; i++) {
+        char *c = (char *)keep(malloc(strlen(names[i]) + 1));
+        strcpy(c, names[i]);
+        copy[i] = c;
+    }
+    s->names = copy;
     return s;
 }
 SEXP PROTECT(SEXP s) { g_protect++; return s; }

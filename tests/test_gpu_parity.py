@@ -161,23 +161,38 @@ def test_near_separation_fuzz_case():
 
 def test_cells_on_and_off_agree(monkeypatch):
     """All-discrete designs run on contingency tables (fit_cell.cuh); ABN_B200_NO_CELLS=1 sends them through
-    the streaming kernels instead. Same flags, same scores to 1e-10 (different summation, same fixed point)."""
+    the streaming kernels instead, ABN_B200_NO_CELL_CAPS=1 keeps the tables but bins every code (no overflow
+    lists, so designs with two or three count parents stream). Same flags, same scores to 1e-10 (different
+    summation, same fixed point), and all three against the oracle."""
     names, data, dists, mp, _ = synth.make_config(4, n=30000, n_nodes=12)
     d = len(names)
     for method in ("mle", "bayes"):
         P = prep.prepare(data, dists, method)
         ch0, par = abncache.enumerate_candidates(d, np.zeros((d, d), int), np.zeros((d, d), int), 3)
         ctrl = H.control(method, d)
-        on = H.gpu_score(P, ch0, par, ctrl)
+        with abncache.DeviceData(P) as dev:
+            on = dev.score(ch0, par, ctrl)
+            kern_on = {k["name"]: k["fits"] for k in dev.timing()["kernels"]}
+        monkeypatch.setenv("ABN_B200_NO_CELL_CAPS", "1")
+        with abncache.DeviceData(P) as dev:
+            nocap = dev.score(ch0, par, ctrl)
+            kern_nocap = {k["name"]: k["fits"] for k in dev.timing()["kernels"]}
+        monkeypatch.delenv("ABN_B200_NO_CELL_CAPS")
         monkeypatch.setenv("ABN_B200_NO_CELLS", "1")
         off = H.gpu_score(P, ch0, par, ctrl)
         monkeypatch.delenv("ABN_B200_NO_CELLS")
-        assert np.array_equal(on["status"], off["status"])
-        assert H.rel_err(on["mlik"], off["mlik"]).max() < 1e-10
+        ref = H.oracle_score(P, ch0, par, ctrl)
+        for other in (nocap, off):
+            assert np.array_equal(on["status"], other["status"])
+            assert H.rel_err(on["mlik"], other["mlik"]).max() < 1e-10
+        assert np.array_equal(on["status"], ref["status"]) and H.rel_err(on["mlik"], ref["mlik"]).max() < TOL
         fam = P.node_family
         discrete = np.array([fam[c] != capi.GAUSSIAN and all(p < 0 or fam[p] != capi.GAUSSIAN for p in ps)
                              for c, ps in zip(ch0, par)])
-        assert discrete.sum() > 100 and not np.array_equal(on["mlik"][discrete], off["mlik"][discrete])  # the path was taken
+        cells = lambda kk: sum(v for k, v in kk.items() if k.startswith("fit_cell_kernel"))
+        assert cells(kern_on) == discrete.sum()                # with capped count columns every all-discrete design qualifies
+        assert 100 < cells(kern_nocap) < cells(kern_on)         # without the caps the wide count columns do not fit
+        assert not np.array_equal(on["mlik"][discrete], off["mlik"][discrete])  # the path was taken
 
 
 @pytest.mark.parametrize("cfg,method", [(3, "mle"), (4, "mle"), (4, "bayes")])
