@@ -10,10 +10,10 @@
 // instructions per row instead of ~40 mixed ones per row and pass) - and then runs the unchanged solver
 // state machine (solver.cuh) with passes over <= 4096 weighted cells instead of n rows.
 //
-//   binomial child (either method): cells over (y, parent pattern); each cell is one evaluation of the
-//       careful row op (RowOp<KIND>, rho always on) times its count - the reference's arithmetic per
-//       distinct row, no shortcuts (the passes cost nothing, so the fit iterates exactly as the reference
-//       does: solver.cuh sees has_gl = 0)
+//   binomial child (either method): cells over (y, parent pattern). Designs with an intercept use the lean row
+//       op and the Gram identities of lean_pass_bin (the solver's shortcuts apply); a fit that meets an eta
+//       outside that row op's range switches to the careful one - the reference's arithmetic per distinct
+//       (y, x), rho correction always on - for the rest of its passes
 //   Poisson child: cells over the parent pattern only; X'y comes from the global Gram matrix
 //       (g = X'y - sum N E x, ll = beta'X'y - sum N E, see warp_pass_pois)
 //
@@ -242,61 +242,71 @@ __device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPla
     *n_ovf = novf;
 }
 
-// one "data pass" over the cells. acc gets the same sums a row pass would produce.
-template <int KIND>
-__device__ __forceinline__ void cell_pass(const DataMeta &m, const CellPlan &cp, const unsigned *cnt, const unsigned *ovf,
-                                          int k, const double *beta_sm, const double *xty, int mode, const RowConst rc,
-                                          PassAcc *acc_sm)
+// One "data pass" over the cells (weight = count) and the overflow rows (weight 1). acc gets the sums a row pass
+// would produce. K = design columns (compile time: the accumulators live in registers).
+//   LEAN (binomial, designs with an intercept): the row op and the Gram identities of lean_pass_bin - sigma, w and
+//     log(1 + e) do not depend on the response, X'y and X'1 come from the Gram matrix - so the solver's shortcuts
+//     apply (has_gl) and the fit needs ~2 passes; returns false when some eta leaves the range the fast row op is
+//     exact for (eta >= 12 for mle: the reference's rho noise; |eta| >= 700 for bayes), and the careful variant
+//     redoes the pass: the reference's arithmetic per distinct (y, x) with the rho correction always on.
+//   Poisson: H = sum N E x x', score and log-likelihood from X'y as in warp_pass_pois.
+template <int KIND, int K, bool LEAN>
+__device__ __forceinline__ bool cell_pass(const DataMeta &m, const CellPlan &cp, const unsigned *cnt, const unsigned *ovf,
+                                          const double *beta_sm, const double *xty, const double *xt1, int mode,
+                                          const RowConst rc, PassAcc *acc_sm)
 {
+    constexpr int NH = K * (K + 1) / 2;
+    constexpr bool MLE_ = (KIND == RK_BIN_MLE);
     const int lane = threadIdx.x & 31;
     const bool need_h = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_HESS);
     const bool need_g = (mode == PASS_FULL || mode == PASS_HG || mode == PASS_GRAD);
     const bool need_l = (mode == PASS_FULL || mode == PASS_LL);
-    double beta[MAXK], H[NTRI], g[MAXK], ll = 0.0;
+    double beta[K], H[NH], g[K], ll = 0.0;
 #pragma unroll
-    for (int j = 0; j < MAXK; j++) { beta[j] = j < k ? beta_sm[j] : 0.0; g[j] = 0.0; }
+    for (int j = 0; j < K; j++) { beta[j] = beta_sm[j]; g[j] = 0.0; }
 #pragma unroll
-    for (int j = 0; j < NTRI; j++) H[j] = 0.0;
+    for (int j = 0; j < NH; j++) H[j] = 0.0;
     RowTrack tk = row_track_init();
     const int ncell = 1 << cp.total_bits;
-    // the cells first, then the rows of the overflow list (codes beyond a cap), one "row" each with weight 1
     const int nunit = ncell + (int)cp.n_ovf;
     for (int u = lane; u < nunit; u += 32) {
-        double dn, x[MAXK], y = 0.0;
+        double dn, x[K], y = 0.0;
         if (u < ncell) {
             const unsigned N = cnt[u];
             if (N == 0) continue;
             dn = (double)N;
 #pragma unroll
-            for (int j = 0; j < MAXK; j++) {
-                x[j] = 0.0;
-                if (j < k) {
-                    const int s = cp.xslot[j];
-                    x[j] = s < 0 ? 1.0 : (double)((u >> cp.shift[s]) & ((1 << cp.bits[s]) - 1));
-                }
+            for (int j = 0; j < K; j++) {
+                const int sl = cp.xslot[j];
+                x[j] = sl < 0 ? 1.0 : (double)((u >> cp.shift[sl]) & ((1 << cp.bits[sl]) - 1));
             }
             y = (double)(u & 1); // the response is the first bit field of a binomial cell
         } else {
             const long long row = ovf[u - ncell];
             dn = 1.0;
 #pragma unroll
-            for (int j = 0; j < MAXK; j++) {
-                x[j] = 0.0;
-                if (j < k) {
-                    const int s = cp.xslot[j];
-                    x[j] = s < 0 ? 1.0 : (double)m.Xq[(long long)cp.col[s] * m.ldq + row];
-                }
+            for (int j = 0; j < K; j++) {
+                const int sl = cp.xslot[j];
+                x[j] = sl < 0 ? 1.0 : (double)m.Xq[(long long)cp.col[sl] * m.ldq + row];
             }
             if (KIND != RK_POIS) y = (double)m.Xq[(long long)cp.col[0] * m.ldq + row];
         }
         double eta = 0.0;
 #pragma unroll
-        for (int j = 0; j < MAXK; j++) eta = fma(x[j], beta[j], eta);
+        for (int j = 0; j < K; j++) eta = fma(x[j], beta[j], eta);
         double w = 0.0, r = 0.0, l = 0.0;
         if (KIND == RK_POIS) {
             row_track(tk, eta);
             const double E = fast_exp(clamp_lo700(eta), rc.tab);
             w = E; r = E; l = E; // r, l: the parts that are summed per cell; X'y is added below
+        } else if (LEAN) {
+            row_track(tk, eta);
+            const double e = fast_exp(-clamp700(eta), rc.tab);
+            const double d = 1.0 + e;
+            const double gg = fast_rcp_approx(d);
+            w = fma(-gg, gg, gg);
+            r = gg;                                  // S = sum g x
+            if (need_l) l = fast_log_ge1(d, rc.logtab); // L = sum log(1 + e)
         } else {
             RowOp<KIND>::template apply<true, true, true>(eta, y, rc, w, r, l, tk, true);
         }
@@ -304,61 +314,89 @@ __device__ __forceinline__ void cell_pass(const DataMeta &m, const CellPlan &cp,
         if (need_h) {
             int t = 0;
 #pragma unroll
-            for (int p = 0; p < MAXK; p++) {
+            for (int p = 0; p < K; p++) {
                 const double wx = w * x[p];
 #pragma unroll
-                for (int q = p; q < MAXK; q++) { H[t] = fma(wx, x[q], H[t]); t++; }
+                for (int q = p; q < K; q++) { H[t] = fma(wx, x[q], H[t]); t++; }
             }
         }
         if (need_g) {
 #pragma unroll
-            for (int p = 0; p < MAXK; p++) g[p] = fma(r, x[p], g[p]);
+            for (int p = 0; p < K; p++) g[p] = fma(r, x[p], g[p]);
         }
         if (need_l) ll += l;
     }
+    if (LEAN) {
+        const int out_of_range = MLE_ ? ((tk.smax >= 0x40280000) | (tk.umax >= 0xC0762E42u))
+                                      : ((tk.smax >= 0x4085E000) | (tk.umax >= 0xC085E000u));
+        if (__any_sync(0xffffffffu, out_of_range)) return false;
+    }
     if (need_h) {
 #pragma unroll
-        for (int j = 0; j < NTRI; j++) H[j] = warp_sum(H[j]);
+        for (int j = 0; j < NH; j++) H[j] = warp_sum(H[j]);
     }
     if (need_g) {
 #pragma unroll
-        for (int j = 0; j < MAXK; j++) g[j] = warp_sum(g[j]);
+        for (int j = 0; j < K; j++) g[j] = warp_sum(g[j]);
     }
     if (need_l) ll = warp_sum(ll);
-    const int bad = __any_sync(0xffffffffu, RowOp<KIND>::bad_of(tk));
+    const int bad = LEAN ? 0 : __any_sync(0xffffffffu, RowOp<KIND>::bad_of(tk));
     if (lane == 0) {
-        // static register indices, run-time shared-memory addresses (the solver wants the packed k x k triangle)
         if (need_h) {
-            int t = 0;
 #pragma unroll
-            for (int p = 0; p < MAXK; p++) {
-#pragma unroll
-                for (int q = p; q < MAXK; q++) {
-                    if (q < k) acc_sm->H[tri(p, q, k)] = H[t];
-                    t++;
-                }
-            }
+            for (int j = 0; j < NH; j++) acc_sm->H[j] = H[j];
         }
         if (need_g) {
 #pragma unroll
-            for (int j = 0; j < MAXK; j++)
-                if (j < k) acc_sm->g[j] = (KIND == RK_POIS) ? xty[j] - g[j] : g[j];
+            for (int j = 0; j < K; j++) {
+                if (KIND == RK_POIS) acc_sm->g[j] = xty[j] - g[j];
+                else if (LEAN) {
+                    const double dbp = rc.bp1 - rc.bp0;
+                    acc_sm->g[j] = MLE_ ? fma(dbp, xty[j], rc.bp0 * xt1[j]) - g[j] : xty[j] - g[j];
+                    if (MLE_) acc_sm->gl[j] = xty[j] - g[j];
+                } else acc_sm->g[j] = g[j];
+            }
         }
         double lsum = 0.0;
         if (need_l) {
             if (KIND == RK_POIS) {
                 lsum = -ll;
 #pragma unroll
-                for (int j = 0; j < MAXK; j++)
-                    if (j < k) lsum = fma(beta[j], xty[j], lsum);
+                for (int j = 0; j < K; j++) lsum = fma(beta[j], xty[j], lsum);
+            } else if (LEAN) {
+                lsum = -ll;
+#pragma unroll
+                for (int j = 0; j < K; j++) lsum = fma(beta[j], xty[j] - xt1[j], lsum);
             } else {
                 lsum = ll;
             }
         }
         acc_sm->ll = lsum;
         acc_sm->bad = bad;
-        acc_sm->has_gl = 0;
+        acc_sm->has_gl = (LEAN && MLE_ && need_g) ? 1 : 0;
     }
+    return true;
+}
+
+// run-time design width -> compile-time K; binomial designs with an intercept try the lean variant first
+template <int KIND>
+__device__ __forceinline__ void cell_pass_any(const DataMeta &m, const CellPlan &cp, const unsigned *cnt, const unsigned *ovf,
+                                              int k, bool icpt, const double *beta_sm, const double *xty, const double *xt1,
+                                              int mode, const RowConst rc, PassAcc *acc_sm, int &careful)
+{
+#define ABN_CELL_CASE(KK)                                                                                              \
+    case KK:                                                                                                           \
+        if (KIND != RK_POIS && icpt && !careful) {                                                                    \
+            if (cell_pass<KIND, KK, true>(m, cp, cnt, ovf, beta_sm, xty, xt1, mode, rc, acc_sm)) return;              \
+            careful = 1;                                                                                               \
+        }                                                                                                              \
+        cell_pass<KIND, KK, false>(m, cp, cnt, ovf, beta_sm, xty, xt1, mode, rc, acc_sm);                              \
+        return;
+    switch (k) {
+        ABN_CELL_CASE(1) ABN_CELL_CASE(2) ABN_CELL_CASE(3) ABN_CELL_CASE(4)
+        ABN_CELL_CASE(5) ABN_CELL_CASE(6) ABN_CELL_CASE(7) ABN_CELL_CASE(8)
+    }
+#undef ABN_CELL_CASE
 }
 
 template <int KIND, int CAPBITS>
@@ -369,7 +407,7 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
     __shared__ FitState st_all[CELL_WARPS];
     __shared__ PassAcc acc_all[CELL_WARPS];
     __shared__ CellPlan plan_all[CELL_WARPS];
-    __shared__ double xty_all[CELL_WARPS][MAXK];
+    __shared__ double xty_all[CELL_WARPS][2 * MAXK]; // (X'y)_j and (X'1)_j of the fit in flight
     __shared__ double exp_tab[ABN_EXP2_N];
     __shared__ double log_tab[128];
     constexpr int CAP = 1 << CAPBITS;
@@ -414,7 +452,10 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
             cp.total_bits = sh;
             cp.n_ovf = 0;
             const long long gy = gram_col(d.ycol);
-            for (int j = 0; j < k; j++) xty[j] = m.G[(long long)gidx(d, j) * m.D + gy];
+            for (int j = 0; j < k; j++) {
+                xty[j] = m.G[(long long)gidx(d, j) * m.D + gy];
+                xty[MAXK + j] = m.G[(long long)gidx(d, j) * m.D];
+            }
         }
         __syncwarp();
         const int tb = cp.total_bits;
@@ -475,8 +516,10 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
         }
         mode = __shfl_sync(0xffffffffu, mode, 0);
         __syncwarp();
+        int careful = 0;
+        const bool icpt = d.cols[0] < 0;
         while (mode != PASS_DONE) {
-            cell_pass<KIND>(m, cp, tab, ovf, k, st.x, xty, mode, rc, acc);
+            cell_pass_any<KIND>(m, cp, tab, ovf, k, icpt, st.x, xty, xty + MAXK, mode, rc, acc, careful);
             __syncwarp();
             if (lane == 0) mode = fit_consume(st, c, *acc);
             mode = __shfl_sync(0xffffffffu, mode, 0);
