@@ -37,8 +37,8 @@ cudaError_t abn_cell_launch(int kind, int large, const abnc::DataMeta &m, const 
 constexpr int BUCKET_SLOT_INTS = 16;
 
 // FP64 instructions one observation row costs in a pass of the streaming kernels, by row kind, design width and pass
-// mode - counted from the SASS of the lean passes (profiles/sass_r2_*; e.g. Poisson K = 4: 3 eta + 9 exp + 13 H = 25,
-// binomial K = 4 HG: 3 + 9 + 1 + 3 rcp + 1 w + 13 H + 4 S = 34). The rare careful / no-intercept passes are
+// mode - counted from the SASS of the lean passes (profiles/sass_r2_*; e.g. Poisson K = 4: 3 eta + 8 exp + 13 H = 24,
+// binomial K = 4 HG: 3 + 8 + 1 + 2 rcp + 1 w + 13 H + 4 S = 32). The rare careful / no-intercept passes are
 // counted with the same formula.
 static int fp64_per_row(int fam /*0 binomial, 1 Poisson*/, int k, int mode)
 {
@@ -47,11 +47,11 @@ static int fp64_per_row(int fam /*0 binomial, 1 Poisson*/, int k, int mode)
     const bool need_l = (mode == PASS_FULL || mode == PASS_LL);
     const int kd = k > 0 ? k - 1 : 0;
     const int hsum = 1 + 2 * kd + k * kd / 2; // w; w x_q; (w x_p); (w x_p) x_q
-    int c = kd + 9 + (ABN_EXP_REPLICATED ? 1 : 0); // eta, exp
+    int c = kd + (ABN_EXP_REPLICATED ? 10 : (ABN_LEAN_EXP1 ? 8 : 9)); // eta, exp
     if (fam == 1) return c + (need_h ? hsum : (need_g ? 1 + kd : 1));
     c += 1;                                   // d = 1 + e
     if (need_l) c += 13;                      // log(1 + e) and its sum
-    if (need_h || need_g) c += 3;             // reciprocal
+    if (need_h || need_g) c += ABN_LEAN_RCP1 ? 2 : 3; // reciprocal
     if (need_h) c += 1 + hsum;
     if (need_g) c += 1 + kd;
     return c;

@@ -163,6 +163,29 @@ ABN_HD double fast_exp256(double t, const double *tab)
     return fma(ts, p, ts);
 }
 
+// The same with ONE reduction step: r = t - n * fl(ln2/256) in a single fma (the product is exact inside the fma).
+// The double nearest to ln2/256 is off by |delta| <= 2.2e-19, so r - and exp(t) relatively - is off by n * delta
+// <= 6e-14 at |t| = 700 and <= 2e-15 for |t| <= 20: this computes exp((1 + kappa) t) with |kappa| <= 8e-17, a
+// perturbation that is uniform in t and therefore invisible to a maximum-likelihood fit (it rescales every linear
+// predictor by the same 1 + kappa). 8 FP64 instructions. Used by the lean passes only.
+ABN_HD double fast_exp256s(double t, const double *tab)
+{
+    const double MAGIC = 6755399441055744.0;
+    const double INV = 369.329833984375;
+    const double LN2_256 = 0.0027076061740622863;    // ln2 / 256 rounded to nearest
+    const double C4 = 0.041666656732559204;
+    const double kd = fma(t, INV, MAGIC);
+    const double nf = kd - MAGIC;
+    const double r = fma(nf, -LN2_256, t);
+    const int n = (int)(uint32_t)double_to_bits(kd);
+    double p = fma(r, C4, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p * r, r, r);
+    const double tj = tab[n & 255];
+    const double ts = with_hi_word(tj, hi_word(tj) + (int)((uint32_t)n << 12));
+    return fma(ts, p, ts);
+}
+
 // ---- exp for the lean passes, bank-conflict-free: 64-entry table, 16 interleaved replicas -------------------
 // A lane-dependent 8-byte table read costs as many shared-memory wavefronts as lanes collide on a bank pair:
 // ~9 per warp for a 256-entry table (ncu, round 2) - 40 % of all shared-memory traffic of the K = 4 Poisson
@@ -225,6 +248,21 @@ ABN_HD double fast_rcp_approx(double d)
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
     double e = fma(-d, x, 1.0);
     e = fma(e, e, e);
+    return fma(x, e, x);
+#else
+    return 1.0 / d;
+#endif
+}
+
+// 1 / d with one Newton step on the MUFU seed: relative error <= seed^2 (~1e-12 .. 1e-14). For the lean binomial
+// passes: g = 1 / (1 + e) enters only the sums S = sum g x and w = g - g^2, where such an error moves the fixed point
+// of the IRLS by its own size - four orders under the parity bar - and the log term does not use it.
+ABN_HD double fast_rcp_newton1(double d)
+{
+#if defined(__CUDA_ARCH__)
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    const double e = fma(-d, x, 1.0);
     return fma(x, e, x);
 #else
     return 1.0 / d;

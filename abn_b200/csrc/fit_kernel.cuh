@@ -639,8 +639,25 @@ constexpr int LEAN_STAGES = ABN_LEAN_STAGES;
 #define ABN_LEAN_EXP fast_exp64r
 constexpr int LEAN_EXP_DOUBLES = ABN_EXP2_N * ABN_EXP64R_COPIES;
 #else
+// ABN_LEAN_EXP1 = 1: one reduction step (fast_exp256s, 8 FP64 instructions; see fastmath.cuh for why that is harmless)
+#ifndef ABN_LEAN_EXP1
+#define ABN_LEAN_EXP1 1
+#endif
+#if ABN_LEAN_EXP1
+#define ABN_LEAN_EXP fast_exp256s
+#else
 #define ABN_LEAN_EXP fast_exp256
+#endif
 constexpr int LEAN_EXP_DOUBLES = ABN_EXP256_N;
+#endif
+// reciprocal of the lean binomial row op: 1 = one Newton step on the MUFU seed (2 FP64), 0 = the cubic step (3 FP64)
+#ifndef ABN_LEAN_RCP1
+#define ABN_LEAN_RCP1 1
+#endif
+#if ABN_LEAN_RCP1
+#define ABN_LEAN_RCP fast_rcp_newton1
+#else
+#define ABN_LEAN_RCP fast_rcp_approx
 #endif
 constexpr int LEAN_TROWS = 128;
 
@@ -919,7 +936,7 @@ __device__ __forceinline__ bool lean_pass_bin(const double *const (&cp)[MAXK], c
         const double d = 1.0 + e;
         if (NEED_L) L += fast_log_ge1(d, rc.logtab);
         if (NEED_H || NEED_G) {
-            const double g = fast_rcp_approx(d);
+            const double g = ABN_LEAN_RCP(d);
             if (NEED_H) {
                 const double w = fma(-g, g, g);
                 H[0] += w;

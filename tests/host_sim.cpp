@@ -287,3 +287,12 @@ extern "C" void sim_fast_exp256(const double *t, double *out, long n)
     if (!done) { for (int j = 0; j < ABN_EXP256_N; j++) tab[j] = exp256_entry(h_exp2_256_table[j], j); done = true; }
     for (long i = 0; i < n; i++) out[i] = fast_exp256(t[i], tab);
 }
+
+// ... and its single-reduction-step form (fast_exp256s)
+extern "C" void sim_fast_exp256s(const double *t, double *out, long n)
+{
+    static double tab[ABN_EXP256_N];
+    static bool done = false;
+    if (!done) { for (int j = 0; j < ABN_EXP256_N; j++) tab[j] = exp256_entry(h_exp2_256_table[j], j); done = true; }
+    for (long i = 0; i < n; i++) out[i] = fast_exp256s(t[i], tab);
+}

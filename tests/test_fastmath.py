@@ -62,6 +62,27 @@ def test_fast_exp64r_about_one_ulp_over_the_working_range():
     assert got[-8] == 1.0 and got[-7] == 1.0
 
 
+def test_fast_exp256s_is_exp_of_a_uniformly_rescaled_argument():
+    """fast_exp256s (lean passes, one reduction step): the error is n * delta with n = round(256 t / ln 2) and
+    |delta| <= 2.2e-19, i.e. it computes exp((1 + kappa) t), |kappa| <= 8e-17: <= 6e-14 relative at |t| = 700, a few
+    ulp for |t| <= 20, and once the common factor is taken out the usual ~1 ulp."""
+    lib = H.sim_lib()
+    lib.sim_fast_exp256s.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_long]
+    rng = np.random.default_rng(4)
+    t = np.concatenate([rng.uniform(-700, 700, 200_000), rng.uniform(-20, 20, 200_000), np.array([0.0, -0.0])])
+    got = np.empty_like(t)
+    lib.sim_fast_exp256s(t.ctypes.data_as(C.POINTER(C.c_double)), got.ctypes.data_as(C.POINTER(C.c_double)), len(t))
+    ref = np.exp(t.astype(np.longdouble))
+    rel = np.abs((got.astype(np.longdouble) - ref) / ref).astype(np.float64)
+    assert rel.max() < 7e-14
+    assert rel[np.abs(t) <= 20].max() < 3e-15
+    # the structured part: rel error / t is (nearly) one constant kappa
+    big = np.abs(t) > 100
+    kappa = ((got.astype(np.longdouble) - ref) / ref / t.astype(np.longdouble))[big].astype(np.float64)
+    assert np.abs(kappa).max() < 1e-16 and kappa.std() < 2e-18
+    assert got[-2] == 1.0 and got[-1] == 1.0
+
+
 def test_fast_exp_exact_points():
     got = _fast_exp(np.array([0.0, math.log(2.0) * 0]))
     assert got[0] == 1.0
