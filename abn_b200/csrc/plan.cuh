@@ -62,6 +62,47 @@ ABN_HD void gram_block(const DataMeta &m, const FitDesc &d, int j0, int k, doubl
             A_(A, i, j) = m.G[(long long)gidx(d, j0 + i) * m.D + gidx(d, j0 + j)];
 }
 
+// Cheap sufficient test for full rank, taken before the eigenvalue test: remove the intercept (rank [1 | X] =
+// 1 + rank of the centred X), scale to unit diagonal and run a Cholesky factorisation; if every pivot of that
+// correlation matrix stays above 1e-4 the design is far from any rank decision (the reference's SVD rule only
+// drops a singular value below max(n, k) eps sigma_max) and the answer is k. This settles all but a handful of the
+// 1e7 candidates of a cache with ~k^3 / 3 flops instead of Jacobi sweeps, and - being invariant to the location
+// and scale of the columns - it also gives the reference's answer for an uncentred column with |mean| >> sd, which
+// the eigenvalue test on raw moments below would call collinear with the intercept.
+ABN_HDN bool gram_full_rank_fast(const double *A, int k, bool icpt_first)
+{
+    double C[MAXM * MAXM];
+    const int o = icpt_first ? 1 : 0, k1 = k - o;
+    if (icpt_first && !(A_(A, 0, 0) > 0.0)) return false;
+    for (int i = 0; i < k1; i++)
+        for (int j = 0; j <= i; j++) {
+            double c = A_(A, o + i, o + j);
+            if (icpt_first) c -= A_(A, 0, o + i) * A_(A, 0, o + j) / A_(A, 0, 0);
+            A_(C, i, j) = c;
+        }
+    double sc[MAXM];
+    for (int i = 0; i < k1; i++) {
+        const double dgi = A_(C, i, i);
+        if (!(dgi > 0.0) || !isfinite(dgi)) return false;
+        // a centred second moment that is mostly cancellation (|mean| > ~1e5 sd) is not trusted here
+        if (icpt_first && dgi < 1e-10 * A_(A, o + i, o + i)) return false;
+        sc[i] = 1.0 / sqrt(dgi);
+    }
+    for (int j = 0; j < k1; j++) {
+        double s = 1.0; // unit diagonal after scaling
+        for (int t = 0; t < j; t++) s -= A_(C, j, t) * A_(C, j, t);
+        if (!(s > 1e-4)) return false;
+        const double l = sqrt(s);
+        A_(C, j, j) = l;
+        for (int i = j + 1; i < k1; i++) {
+            double v = A_(C, i, j) * sc[i] * sc[j];
+            for (int t = 0; t < j; t++) v -= A_(C, i, t) * A_(C, j, t);
+            A_(C, i, j) = v / l;
+        }
+    }
+    return true;
+}
+
 // arma::rank of the n x k design from the eigenvalues of its Gram block: singular values
 // sqrt(lambda_i) against max(n,k) * sigma_max * eps, with the floor FP64 accumulation of the
 // Gram imposes on what can be told from zero.
@@ -70,6 +111,7 @@ ABN_HDN int gram_rank(const DataMeta &m, const FitDesc &d, int j0, int k)
     if (k <= 0) return 0;
     double A[MAXM * MAXM], V[MAXM * MAXM], w[MAXM];
     gram_block(m, d, j0, k, A);
+    if (gram_full_rank_fast(A, k, gidx(d, j0) == 0)) return k;
     jacobi_eig(A, k, w, V);
     double lmax = 0.0;
     for (int i = 0; i < k; i++) if (w[i] > lmax) lmax = w[i];

@@ -90,8 +90,14 @@ def main():
         if world > 1:
             dist.barrier()
         t2 = time.time()
-        res = dev.score(ch0[idx], par[idx], ctrl)
-        score_local_s = time.time() - t2
+        if world == 1 and not args.limit:
+            # the product path of buildScoreCache: candidates generated on the device, nothing uploaded
+            res = dev.score_enumerated(zero, zero, mp, ctrl)
+            score_local_s = time.time() - t2
+            assert np.array_equal(res["children"], ch0) and np.array_equal(res["parents"], par)
+        else:
+            res = dev.score(ch0[idx], par[idx], ctrl)
+            score_local_s = time.time() - t2
         timing = dev.timing()
     gather_s = 0.0
     if world > 1:
