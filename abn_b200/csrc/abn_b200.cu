@@ -331,6 +331,19 @@ col_tail_kernel(const unsigned char *__restrict__ Xq, long long ldq, long long n
     if (threadIdx.x < 8 && acc[threadIdx.x]) atomicAdd(&col_tail[col * 8 + threadIdx.x], acc[threadIdx.x]);
 }
 
+// bit planes of the binary columns (fit_cell.cuh cell_count_planes): one word per warp, all ldb words of a column
+// are written (zero beyond n and for columns that are not binary)
+__global__ void bitplane_kernel(const unsigned char *__restrict__ Xq, long long ldq, long long n, const int *__restrict__ col_card,
+                                unsigned *__restrict__ Xb, long long ldb)
+{
+    const int col = blockIdx.y;
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int card = col_card[col];
+    const bool bit = (card == 1 || card == 2) && r < n && (Xq[(long long)col * ldq + r] & 1u);
+    const unsigned w = __ballot_sync(0xffffffffu, bit);
+    if ((threadIdx.x & 31) == 0 && (r >> 5) < ldb) Xb[(long long)col * ldb + (r >> 5)] = w;
+}
+
 __global__ void col_card_kernel(int n_cols, const int *__restrict__ col_bad, const int *__restrict__ col_max, int *__restrict__ col_card)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -429,6 +442,8 @@ struct abn_data {
     double *dX = nullptr, *dG = nullptr, *dLfact = nullptr;
     int *dFamily = nullptr, *dCol0 = nullptr, *dGwIndex = nullptr, *dPoisNode = nullptr;
     unsigned char *dXq = nullptr; // byte codes of the discrete columns (fit_cell.cuh)
+    unsigned *dXb = nullptr;      // bit planes of the binary ones
+    long long ldb = 0;
     int *dColCard = nullptr;
     unsigned *dColTail = nullptr, *dCellOvf = nullptr; // capped codes: tail counts, overflow lists
     double *dGc = nullptr, *dColMean = nullptr; // centred Gram and the shifts it was built with ([0] = 0)
@@ -468,7 +483,7 @@ extern "C" void abn_b200_data_destroy(abn_data *d)
     free_scratch(d);
     dev_free(d->dX, d->stream); dev_free(d->dG, d->stream); dev_free(d->dLfact, d->stream); dev_free(d->dFamily, d->stream); dev_free(d->dCol0, d->stream);
     dev_free(d->dGwIndex, d->stream); dev_free(d->dPoisNode, d->stream);
-    dev_free(d->dXq, d->stream); dev_free(d->dColCard, d->stream);
+    dev_free(d->dXq, d->stream); dev_free(d->dXb, d->stream); dev_free(d->dColCard, d->stream);
     dev_free(d->dColTail, d->stream); dev_free(d->dCellOvf, d->stream);
     dev_free(d->dGc, d->stream); dev_free(d->dColMean, d->stream);
     dev_free(d->dBucketStart, d->stream); dev_free(d->dCounters, d->stream);
@@ -609,6 +624,10 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     const bool use_cells = !(no_cells && *no_cells && *no_cells != '0');
     if (use_cells) {
         TRY_OR_FREE(dev_alloc(&d->dXq, (size_t)ld * ds->n_cols, d->stream));
+        d->ldb = ((ds->n + 31) / 32 + 3) / 4 * 4;
+        const char *no_planes = std::getenv("ABN_B200_NO_BITPLANES");
+        if (!(no_planes && *no_planes && *no_planes != '0'))
+            TRY_OR_FREE(dev_alloc(&d->dXb, (size_t)d->ldb * ds->n_cols * sizeof(unsigned), d->stream));
         TRY_OR_FREE(dev_alloc(&d->dColCard, (size_t)ds->n_cols * 3 * sizeof(int), d->stream)); // card | bad | max
         TRY_OR_FREE(dev_alloc(&d->dColTail, (size_t)ds->n_cols * 8 * sizeof(unsigned), d->stream));
         // overflow lists of the capped contingency tables: n / 8 rows per resident warp (3.5 GB for n = 1e6 on 148 SMs);
@@ -648,6 +667,8 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
     d->m.Xq = nullptr;
     d->m.ldq = ld;
     d->m.col_card = nullptr;
+    d->m.Xb = nullptr;
+    d->m.ldb = 0;
     d->m.col_tail = nullptr;
     d->m.cell_ovf = nullptr;
     d->m.cell_ovf_stride = 0;
@@ -660,6 +681,9 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
             const long long groups = (ds->n + 15) / 16;
             discretize_kernel<<<dim3((unsigned)((groups + 255) / 256), ds->n_cols), 256, 0, d->stream>>>(d->dX, ld, ds->n, d->dXq, ld, bad, mx);
             col_card_kernel<<<(ds->n_cols + 127) / 128, 128, 0, d->stream>>>(ds->n_cols, bad, mx, d->dColCard);
+            if (d->dXb)
+                bitplane_kernel<<<dim3((unsigned)((d->ldb * 32 + 255) / 256), ds->n_cols), 256, 0, d->stream>>>(d->dXq, ld, ds->n, d->dColCard,
+                                                                                                         d->dXb, d->ldb);
             e = cudaMemsetAsync(d->dColTail, 0, (size_t)ds->n_cols * 8 * sizeof(unsigned), d->stream);
             col_tail_kernel<<<dim3((unsigned)((groups + 255) / 256), ds->n_cols), 256, 0, d->stream>>>(d->dXq, ld, ds->n, d->dColTail);
             if (e == cudaSuccess) e = cudaGetLastError();
@@ -669,7 +693,9 @@ extern "C" int abn_b200_data_create(const abn_dataset *ds, int32_t device, abn_d
             abn_b200_data_destroy(d);
             return rc;
         }
-        d->timing.launches += 3;
+        d->timing.launches += d->dXb ? 4 : 3;
+        d->m.Xb = d->dXb;
+        d->m.ldb = d->ldb;
         d->m.Xq = d->dXq;
         d->m.col_card = d->dColCard;
         d->m.col_tail = d->dColTail;

@@ -186,44 +186,6 @@ ABN_HD double fast_exp256s(double t, const double *tab)
     return fma(ts, p, ts);
 }
 
-// U arguments at once, stage by stage: every dependent step of the evaluation is issued for all U values before the
-// next one, so that a warp has U independent FP64 instructions in flight per step (a DFMA result takes ~8 cycles,
-// the pipe accepts one warp instruction every 2: U = 4 covers the latency from a single warp). ONE = fast_exp256s.
-template <int U, bool ONE>
-ABN_HD void fast_exp256_multi(const double (&t)[U], double (&out)[U], const double *tab)
-{
-    const double MAGIC = 6755399441055744.0;
-    const double INV = 369.329833984375;
-    const double LN2_256 = 0.0027076061740622863;
-    const double LN2_256_HI = 0.002707604318857193;
-    const double LN2_256_LO = 1.855205093371747e-09;
-    const double C4 = 0.041666656732559204;
-    double kd[U], r[U], p[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) kd[u] = fma(t[u], INV, MAGIC);
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-        const double nf = kd[u] - MAGIC;
-        if (ONE) r[u] = fma(nf, -LN2_256, t[u]);
-        else { r[u] = fma(nf, -LN2_256_HI, t[u]); r[u] = fma(nf, -LN2_256_LO, r[u]); }
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) p[u] = fma(r[u], C4, 1.0 / 6.0);
-#pragma unroll
-    for (int u = 0; u < U; u++) p[u] = fma(p[u], r[u], 0.5);
-#pragma unroll
-    for (int u = 0; u < U; u++) p[u] = p[u] * r[u];
-#pragma unroll
-    for (int u = 0; u < U; u++) p[u] = fma(p[u], r[u], r[u]);
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-        const int n = (int)(uint32_t)double_to_bits(kd[u]);
-        const double tj = tab[n & 255];
-        const double ts = with_hi_word(tj, hi_word(tj) + (int)((uint32_t)n << 12));
-        out[u] = fma(ts, p[u], ts);
-    }
-}
-
 // ---- exp for the lean passes, bank-conflict-free: 64-entry table, 16 interleaved replicas -------------------
 // A lane-dependent 8-byte table read costs as many shared-memory wavefronts as lanes collide on a bank pair:
 // ~9 per warp for a 256-entry table (ncu, round 2) - 40 % of all shared-memory traffic of the K = 4 Poisson
@@ -304,27 +266,6 @@ ABN_HD double fast_rcp_newton1(double d)
     return fma(x, e, x);
 #else
     return 1.0 / d;
-#endif
-}
-
-// U reciprocals, staged like fast_exp256_multi; STEPS = 1: fast_rcp_newton1, 2: fast_rcp_approx
-template <int U, int STEPS>
-ABN_HD void fast_rcp_multi(const double (&d)[U], double (&out)[U])
-{
-#if defined(__CUDA_ARCH__)
-    double x[U], e[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x[u]) : "d"(d[u]));
-#pragma unroll
-    for (int u = 0; u < U; u++) e[u] = fma(-d[u], x[u], 1.0);
-    if (STEPS > 1) {
-#pragma unroll
-        for (int u = 0; u < U; u++) e[u] = fma(e[u], e[u], e[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) out[u] = fma(x[u], e[u], x[u]);
-#else
-    for (int u = 0; u < U; u++) out[u] = 1.0 / d[u];
 #endif
 }
 

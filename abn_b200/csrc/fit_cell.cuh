@@ -86,6 +86,7 @@ struct CellPlan {
     int xslot[MAXK];     // design column j takes its value from byte column xslot[j] (-1: intercept)
     int cap[MAXK + 1];   // codes >= cap go to the overflow list (256: the column is not capped)
     int any_cap;
+    int all_binary;      // every byte column is binary and the bit planes exist: cell_count_planes
     unsigned n_ovf;      // rows in the overflow list of the fit in flight
 };
 
@@ -240,6 +241,72 @@ __device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPla
         }
     }
     *n_ovf = novf;
+}
+
+// Contingency table of a fit whose byte columns are all BINARY, from the bit planes (DataMeta::Xb): the number of
+// rows on which every plane of a subset S is one is popcount(AND of the planes of S), and the table - rows on which
+// EXACTLY the planes of T are one - follows by inclusion-exclusion. Subsets of fewer than three planes need no data
+// at all (n, column sums and pair counts are entries of the global Gram matrix, exact integers in FP64), so a
+// binomial child with four binary parents costs 16 AND + 16 POPC + 16 adds per 32 ROWS and lane, in registers, with
+// no dependent shared-memory update anywhere (cell_count_rows: ~8 instructions and a ~35-cycle chain per row).
+// All integer work: the table is the one cell_count_rows builds, bit for bit.
+__host__ __device__ constexpr int cell_popc(int x) { return x == 0 ? 0 : (x & 1) + cell_popc(x >> 1); }
+__host__ __device__ constexpr int cell_ctz(int x) { return (x & 1) ? 0 : 1 + cell_ctz(x >> 1); }
+
+template <int NP>
+__device__ __forceinline__ void cell_count_planes(const DataMeta &m, const CellPlan &cp, unsigned *tab)
+{
+    constexpr int NS = 1 << NP;
+    const int lane = threadIdx.x & 31;
+    const uint4 *pp[NP];
+#pragma unroll
+    for (int j = 0; j < NP; j++) pp[j] = reinterpret_cast<const uint4 *>(m.Xb + (long long)cp.col[j] * m.ldb);
+    unsigned cnt[NS];
+#pragma unroll
+    for (int S = 0; S < NS; S++) cnt[S] = 0u;
+    const long long nq = m.ldb / 4; // 128 rows per 16-byte load; words beyond n are zero
+    for (long long q = lane; q < nq; q += 32) {
+        uint4 v[NP];
+#pragma unroll
+        for (int j = 0; j < NP; j++) v[j] = __ldg(pp[j] + q);
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            unsigned msk[NS];
+            msk[0] = 0xffffffffu;
+#pragma unroll
+            for (int S = 1; S < NS; S++) {
+                const int j = cell_ctz(S), rest = S & (S - 1);
+                const unsigned pj = w == 0 ? v[j].x : (w == 1 ? v[j].y : (w == 2 ? v[j].z : v[j].w));
+                msk[S] = rest ? (msk[rest] & pj) : pj;
+                if (cell_popc(S) >= 3) cnt[S] += __popc(msk[S]);
+            }
+        }
+    }
+#pragma unroll
+    for (int S = 1; S < NS; S++) {
+        if (cell_popc(S) >= 3) {
+            unsigned c = cnt[S];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) tab[S] = c;
+        }
+    }
+    for (int S = lane; S < NS; S += 32) {
+        const int pc = __popc(S);
+        if (pc == 0) tab[S] = (unsigned)m.n;
+        else if (pc <= 2) {
+            const int a = gram_col(cp.col[__ffs(S) - 1]), b = pc == 1 ? 0 : gram_col(cp.col[31 - __clz(S)]);
+            tab[S] = (unsigned)m.G[(long long)a * m.D + b];
+        }
+    }
+    __syncwarp();
+    // f(S) = rows with all planes of S set  ->  g(T) = rows with exactly the planes of T set: plane by plane
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        for (int S = lane; S < NS; S += 32)
+            if (!((S >> i) & 1)) tab[S] -= tab[S | (1 << i)];
+        __syncwarp();
+    }
 }
 
 // One "data pass" over the cells (weight = count) and the overflow rows (weight 1). acc gets the sums a row pass
@@ -438,6 +505,7 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
             if (d.family == BINOMIAL) { cp.col[0] = d.ycol; cp.shift[0] = 0; cp.bits[0] = 1; nc = 1; sh = 1; }
             cp.cap[0] = 256;
             cp.any_cap = 0;
+            int binary = m.Xb != nullptr;
             for (int j = 0; j < k; j++) {
                 if (d.cols[j] < 0) { cp.xslot[j] = -1; continue; }
                 bool capped;
@@ -445,10 +513,12 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
                 cp.col[nc] = d.cols[j]; cp.shift[nc] = sh; cp.bits[nc] = b;
                 cp.cap[nc] = capped ? (1 << b) : 256;
                 cp.any_cap |= capped ? 1 : 0;
+                binary &= m.col_card[d.cols[j]] <= 2;
                 cp.xslot[j] = nc;
                 nc++; sh += b;
             }
             cp.ncol = nc;
+            cp.all_binary = binary && nc <= CELL_SMALL_BITS;
             cp.total_bits = sh;
             cp.n_ovf = 0;
             const long long gy = gram_col(d.ycol);
@@ -459,40 +529,53 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
         }
         __syncwarp();
         const int tb = cp.total_bits;
-        const int lcl = min(5, CAPBITS - tb);       // log2 of the replicas across lanes
-        const int lc = min(7, CAPBITS - tb);        // ... times the sets across rows (cell_count_rows)
-        for (int i = lane; i < (1 << (tb + lc)); i += 32) tab[i] = 0u;
-        __syncwarp();
-        unsigned novf = 0;
-        switch (cp.ncol) {
-        case 0: break;
-        case 1: cell_count_rows<1>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
-        case 2: cell_count_rows<2>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
-        case 3: cell_count_rows<3>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
-        case 4: cell_count_rows<4>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
-        case 5: cell_count_rows<5>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
-        case 6: cell_count_rows<6>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
-        case 7: cell_count_rows<7>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
-        case 8: cell_count_rows<8>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
-        default: cell_count_rows<MAXK + 1>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
-        }
-        __syncwarp();
-        if (lane == 0) cp.n_ovf = novf;
-        // fold the replicas: counter of cell c ends up at tab[c]. Round r handles cells 32 r .. 32 r + 31: all
-        // reads of a round precede its writes, and later rounds read only beyond what has been written
-        if (cp.ncol == 0) {
-            if (lane == 0) tab[0] = (unsigned)m.n; // intercept-only Poisson fit: one cell
-        } else if (lc > 0) {
-            const int copies = 1 << lc;
-            for (int c0 = 0; c0 < (1 << tb); c0 += 32) {
-                const int cc = c0 + lane;
-                unsigned s = 0;
-                if (cc < (1 << tb))
-                    for (int r = 0; r < copies; r++) s += tab[(cc << lc) + r];
-                __syncwarp();
-                if (cc < (1 << tb)) tab[cc] = s;
-                __syncwarp();
+        if (CAPBITS == CELL_SMALL_CAPBITS && cp.all_binary && cp.ncol >= 1) {
+            switch (cp.ncol) {
+            case 1: cell_count_planes<1>(m, cp, tab); break;
+            case 2: cell_count_planes<2>(m, cp, tab); break;
+            case 3: cell_count_planes<3>(m, cp, tab); break;
+            case 4: cell_count_planes<4>(m, cp, tab); break;
+            case 5: cell_count_planes<5>(m, cp, tab); break;
+            default: cell_count_planes<6>(m, cp, tab); break;
             }
+        } else {
+            const int lcl = min(5, CAPBITS - tb);       // log2 of the replicas across lanes
+            const int lc = min(7, CAPBITS - tb);        // ... times the sets across rows (cell_count_rows)
+            for (int i = lane; i < (1 << (tb + lc)); i += 32) tab[i] = 0u;
+            __syncwarp();
+            unsigned novf = 0;
+            switch (cp.ncol) {
+            case 0: break;
+            case 1: cell_count_rows<1>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+            case 2: cell_count_rows<2>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+            case 3: cell_count_rows<3>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+            case 4: cell_count_rows<4>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+            case 5: cell_count_rows<5>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+            case 6: cell_count_rows<6>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+            case 7: cell_count_rows<7>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+            case 8: cell_count_rows<8>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+            default: cell_count_rows<MAXK + 1>(m, cp, tab, CAP, lcl, lc, ovf, &novf); break;
+            }
+            __syncwarp();
+            if (lane == 0) cp.n_ovf = novf;
+            // fold the replicas: counter of cell c ends up at tab[c]. Round r handles cells 32 r .. 32 r + 31: all
+            // reads of a round precede its writes, and later rounds read only beyond what has been written
+            if (cp.ncol == 0) {
+                if (lane == 0) tab[0] = (unsigned)m.n; // intercept-only Poisson fit: one cell
+            } else if (lc > 0) {
+                const int copies = 1 << lc;
+                for (int c0 = 0; c0 < (1 << tb); c0 += 32) {
+                    const int cc = c0 + lane;
+                    unsigned s = 0;
+                    if (cc < (1 << tb))
+                        for (int r = 0; r < copies; r++) s += tab[(cc << lc) + r];
+                    __syncwarp();
+                    if (cc < (1 << tb)) tab[cc] = s;
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+
         }
         __syncwarp();
 

@@ -650,17 +650,6 @@ constexpr int LEAN_EXP_DOUBLES = ABN_EXP2_N * ABN_EXP64R_COPIES;
 #endif
 constexpr int LEAN_EXP_DOUBLES = ABN_EXP256_N;
 #endif
-template <int U>
-__device__ __forceinline__ void lean_exp_multi(const double (&t)[U], double (&out)[U], const double *tab)
-{
-#if ABN_EXP_REPLICATED
-#pragma unroll
-    for (int u = 0; u < U; u++) out[u] = fast_exp64r(t[u], tab);
-#else
-    fast_exp256_multi<U, ABN_LEAN_EXP1 != 0>(t, out, tab);
-#endif
-}
-
 // reciprocal of the lean binomial row op: 1 = one Newton step on the MUFU seed (2 FP64), 0 = the cubic step (3 FP64)
 #ifndef ABN_LEAN_RCP1
 #define ABN_LEAN_RCP1 1
@@ -723,24 +712,22 @@ __device__ __forceinline__ void lean_stream(const double *const (&cp)[MAXK], lon
             const double2 b = *reinterpret_cast<const double2 *>(t + j * TR + 64);
             x[0][j] = a.x; x[1][j] = a.y; x[2][j] = b.x; x[3][j] = b.y;
         }
-        int h[4];
-        row(x, h);
-        tk.smax = max(max(tk.smax, h[0]), h[1]);
-        tk.umax = max(max(tk.umax, (unsigned)h[0]), (unsigned)h[1]);
-        tk.smax = max(max(tk.smax, h[2]), h[3]);
-        tk.umax = max(max(tk.umax, (unsigned)h[2]), (unsigned)h[3]);
+        const int h0 = row(x[0]), h1 = row(x[1]), h2 = row(x[2]), h3 = row(x[3]);
+        tk.smax = max(max(tk.smax, h0), h1);
+        tk.umax = max(max(tk.umax, (unsigned)h0), (unsigned)h1);
+        tk.smax = max(max(tk.smax, h2), h3);
+        tk.umax = max(max(tk.umax, (unsigned)h2), (unsigned)h3);
         fill = stage;
         stage = (stage + 1 == ST) ? 0 : stage + 1;
     }
     cp_async_wait<0>();
     for (long long i = (long long)ntiles * TR + lane; i < n; i += 32) { // fewer than 128 rows (all of them for KD = 0)
-        double xt[1][KDA];
+        double xt[KDA];
 #pragma unroll
-        for (int j = 0; j < KD; j++) xt[0][j] = __ldg(cp[j] + i);
-        int h[1];
-        row(xt, h);
-        tk.smax = max(tk.smax, h[0]);
-        tk.umax = max(tk.umax, (unsigned)h[0]);
+        for (int j = 0; j < KD; j++) xt[j] = __ldg(cp[j] + i);
+        const int h = row(xt);
+        tk.smax = max(tk.smax, h);
+        tk.umax = max(tk.umax, (unsigned)h);
     }
 }
 
@@ -819,24 +806,22 @@ __device__ __forceinline__ void lean_stream_tma(const double *const (&cp)[MAXK],
             const double2 b = *reinterpret_cast<const double2 *>(t + j * TR + 64);
             x[0][j] = a.x; x[1][j] = a.y; x[2][j] = b.x; x[3][j] = b.y;
         }
-        int h[4];
-        row(x, h);
-        tk.smax = max(max(tk.smax, h[0]), h[1]);
-        tk.umax = max(max(tk.umax, (unsigned)h[0]), (unsigned)h[1]);
-        tk.smax = max(max(tk.smax, h[2]), h[3]);
-        tk.umax = max(max(tk.umax, (unsigned)h[2]), (unsigned)h[3]);
+        const int h0 = row(x[0]), h1 = row(x[1]), h2 = row(x[2]), h3 = row(x[3]);
+        tk.smax = max(max(tk.smax, h0), h1);
+        tk.umax = max(max(tk.umax, (unsigned)h0), (unsigned)h1);
+        tk.smax = max(max(tk.smax, h2), h3);
+        tk.umax = max(max(tk.umax, (unsigned)h2), (unsigned)h3);
         fill = stage;
         stage = (stage + 1 == ST) ? 0 : stage + 1;
     }
     __syncwarp();
     for (long long i = (long long)ntiles * TR + lane; i < n; i += 32) {
-        double xt[1][KDA];
+        double xt[KDA];
 #pragma unroll
-        for (int j = 0; j < KD; j++) xt[0][j] = __ldg(cp[j] + i);
-        int h[1];
-        row(xt, h);
-        tk.smax = max(tk.smax, h[0]);
-        tk.umax = max(tk.umax, (unsigned)h[0]);
+        for (int j = 0; j < KD; j++) xt[j] = __ldg(cp[j] + i);
+        const int h = row(xt);
+        tk.smax = max(tk.smax, h);
+        tk.umax = max(tk.umax, (unsigned)h);
     }
 }
 
@@ -869,37 +854,27 @@ __device__ __forceinline__ bool lean_pass_pois(const double *const (&cp)[MAXK], 
 #pragma unroll
     for (int j = 0; j < NH; j++) H[j] = 0.0;
     RowTrack tk = row_track_init();
-    // U rows in lockstep (U = 4 in the tiles, 1 in the tail): every stage for all rows before the next, see
-    // fast_exp256_multi; rows are added to the accumulators in increasing order
-    auto row = [&](const auto &x, auto &h) {
-        constexpr int U = (int)(sizeof(h) / sizeof(int));
-        double eta[U], E[U];
+    auto row = [&](const double (&x)[KDA]) -> int {
+        double eta = beta[0];
 #pragma unroll
-        for (int u = 0; u < U; u++) eta[u] = beta[0];
+        for (int j = 0; j < KD; j++) eta = fma(x[j], beta[j + 1], eta);
+        const double E = ABN_LEAN_EXP(eta, tab256);
+        H[0] += E;
+        if (ALL_H) {
+            int t = 1;
 #pragma unroll
-        for (int j = 0; j < KD; j++)
+            for (int q = 0; q < KD; q++) { H[t] = fma(E, x[q], H[t]); t++; }
 #pragma unroll
-            for (int u = 0; u < U; u++) eta[u] = fma(x[u][j], beta[j + 1], eta[u]);
-        lean_exp_multi<U>(eta, E, tab256);
+            for (int p = 0; p < KD; p++) {
+                const double wx = E * x[p];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            H[0] += E[u];
-            if (ALL_H) {
-                int t = 1;
-#pragma unroll
-                for (int q = 0; q < KD; q++) { H[t] = fma(E[u], x[u][q], H[t]); t++; }
-#pragma unroll
-                for (int p = 0; p < KD; p++) {
-                    const double wx = E[u] * x[u][p];
-#pragma unroll
-                    for (int q = p; q < KD; q++) { H[t] = fma(wx, x[u][q], H[t]); t++; }
-                }
-            } else if (MODE == PASS_GRAD) {
-#pragma unroll
-                for (int q = 0; q < KD; q++) H[q + 1] = fma(E[u], x[u][q], H[q + 1]);
+                for (int q = p; q < KD; q++) { H[t] = fma(wx, x[q], H[t]); t++; }
             }
-            h[u] = hi_word(eta[u]);
+        } else if (MODE == PASS_GRAD) {
+#pragma unroll
+            for (int q = 0; q < KD; q++) H[q + 1] = fma(E, x[q], H[q + 1]);
         }
+        return hi_word(eta);
     };
     lean_rows<KD>(cp, n, tile, pipe, tk, row);
     if (__any_sync(0xffffffffu, (tk.smax >= 0x4085E000) | (tk.umax >= 0xC085E000u))) return false; // |eta| >= 700, NaN
@@ -953,44 +928,35 @@ __device__ __forceinline__ bool lean_pass_bin(const double *const (&cp)[MAXK], c
 #pragma unroll
     for (int j = 0; j < K; j++) S[j] = 0.0;
     RowTrack tk = row_track_init();
-    auto row = [&](const auto &x, auto &h) { // U rows in lockstep, see lean_pass_pois
-        constexpr int U = (int)(sizeof(h) / sizeof(int));
-        double eta[U], t[U], e[U], d[U], g[U];
+    auto row = [&](const double (&x)[KDA]) -> int {
+        double eta = beta[0];
 #pragma unroll
-        for (int u = 0; u < U; u++) eta[u] = beta[0];
-#pragma unroll
-        for (int j = 0; j < KD; j++)
-#pragma unroll
-            for (int u = 0; u < U; u++) eta[u] = fma(x[u][j], beta[j + 1], eta[u]);
-#pragma unroll
-        for (int u = 0; u < U; u++) t[u] = -eta[u];
-        lean_exp_multi<U>(t, e, tab256);
-#pragma unroll
-        for (int u = 0; u < U; u++) d[u] = 1.0 + e[u];
-        if (NEED_H || NEED_G) fast_rcp_multi<U, ABN_LEAN_RCP1 ? 1 : 2>(d, g);
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (NEED_L) L += fast_log_ge1(d[u], rc.logtab);
+        for (int j = 0; j < KD; j++) eta = fma(x[j], beta[j + 1], eta);
+        const double e = ABN_LEAN_EXP(-eta, tab256);
+        const double d = 1.0 + e;
+        if (NEED_L) L += fast_log_ge1(d, rc.logtab);
+        if (NEED_H || NEED_G) {
+            const double g = ABN_LEAN_RCP(d);
             if (NEED_H) {
-                const double w = fma(-g[u], g[u], g[u]);
+                const double w = fma(-g, g, g);
                 H[0] += w;
-                int tt = 1;
+                int t = 1;
 #pragma unroll
-                for (int q = 0; q < KD; q++) { H[tt] = fma(w, x[u][q], H[tt]); tt++; }
+                for (int q = 0; q < KD; q++) { H[t] = fma(w, x[q], H[t]); t++; }
 #pragma unroll
                 for (int p = 0; p < KD; p++) {
-                    const double wx = w * x[u][p];
+                    const double wx = w * x[p];
 #pragma unroll
-                    for (int q = p; q < KD; q++) { H[tt] = fma(wx, x[u][q], H[tt]); tt++; }
+                    for (int q = p; q < KD; q++) { H[t] = fma(wx, x[q], H[t]); t++; }
                 }
             }
             if (NEED_G) {
-                S[0] += g[u];
+                S[0] += g;
 #pragma unroll
-                for (int q = 0; q < KD; q++) S[q + 1] = fma(g[u], x[u][q], S[q + 1]);
+                for (int q = 0; q < KD; q++) S[q + 1] = fma(g, x[q], S[q + 1]);
             }
-            h[u] = hi_word(eta[u]);
         }
+        return hi_word(eta);
     };
     lean_rows<KD>(cp, n, tile, pipe, tk, row);
     const int out_of_range = MLE_ ? ((tk.smax >= 0x40280000) | (tk.umax >= 0xC0762E42u))

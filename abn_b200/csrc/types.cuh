@@ -29,6 +29,10 @@ struct DataMeta {
     const unsigned char *Xq;
     long long ldq;
     const int *col_card;
+    // bit planes of the BINARY columns (col_card <= 2): bit r mod 32 of word r / 32 is the code of row r; ldb words
+    // per column (a multiple of 4), bits beyond n and the planes of other columns are zero. Null: not built.
+    const unsigned *Xb;
+    long long ldb;
     // capped codes: col_tail[c * 8 + b] = rows of column c whose code is >= 2^b (b = 0..7); rows beyond a cap go
     // to the warp's overflow list cell_ovf + slot * cell_ovf_stride (row indices). Null: no capping.
     const unsigned *col_tail;

@@ -195,6 +195,43 @@ def test_cells_on_and_off_agree(monkeypatch):
         assert not np.array_equal(on["mlik"][discrete], off["mlik"][discrete])  # the path was taken
 
 
+def test_bit_plane_tables_are_bit_identical_to_byte_counting(monkeypatch):
+    """All-binary designs build their contingency table from bit planes (popcounts of ANDed planes, pair and
+    single counts from the Gram matrix, inclusion-exclusion: fit_cell.cuh cell_count_planes);
+    ABN_B200_NO_BITPLANES=1 counts the same rows byte code by byte code. Integer tables: every result bit for
+    bit. n is not a multiple of 128 (ragged last words); both methods; a binary child with up to five parents
+    (six planes) and a Poisson child with binary parents."""
+    rng = np.random.default_rng(77)
+    n, nb = 20_077, 8
+    import pandas as pd
+    z = rng.normal(size=n)
+    cols = {f"b{i}": (rng.random(n) < 1 / (1 + np.exp(-(0.4 * z + 0.3 * i - 1)))).astype(float) for i in range(nb)}
+    cols["p0"] = rng.poisson(np.exp(0.3 + 0.4 * cols["b0"] - 0.3 * cols["b1"])).astype(float)
+    data = pd.DataFrame(cols)
+    dists = {c: ("poisson" if c == "p0" else "binomial") for c in data.columns}
+    d = data.shape[1]
+    ban = np.zeros((d, d), int)
+    ban[:, d - 1] = 1                                          # the count node is a child only: every design is all-binary
+    for method in ("mle", "bayes"):
+        P = prep.prepare(data, dists, method)
+        ch0, par = abncache.enumerate_candidates(d, ban, np.zeros((d, d), int), 5)
+        ctrl = H.control(method, d)
+        with abncache.DeviceData(P) as dev:
+            planes = dev.score(ch0, par, ctrl)
+            kern = {k["name"]: k["fits"] for k in dev.timing()["kernels"]}
+        assert sum(v for k, v in kern.items() if k.startswith("fit_cell_kernel")) == len(ch0)
+        monkeypatch.setenv("ABN_B200_NO_BITPLANES", "1")
+        with abncache.DeviceData(P) as dev:
+            counted = dev.score(ch0, par, ctrl)
+        monkeypatch.delenv("ABN_B200_NO_BITPLANES")
+        for k in ("mlik", "status", "iters") + (("aic", "bic", "mdl") if method == "mle" else ()):
+            assert np.array_equal(planes[k], counted[k], equal_nan=(k not in ("status", "iters"))), (method, k)
+        rows = np.sort(rng.choice(len(ch0), size=400, replace=False))
+        ref = H.oracle_score(P, ch0[rows], par[rows], ctrl)
+        assert np.array_equal(planes["status"][rows], ref["status"])
+        assert H.rel_err(planes["mlik"][rows], ref["mlik"]).max() < TOL
+
+
 @pytest.mark.parametrize("cfg,method", [(3, "mle"), (4, "mle"), (4, "bayes")])
 def test_synthetic_small_vs_oracle(cfg, method):
     """Shrunk versions of BASELINE.json configs[2] / configs[3] (same generator, fewer rows / nodes)."""
