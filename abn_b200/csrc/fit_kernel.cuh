@@ -742,6 +742,15 @@ __device__ __forceinline__ void lean_stream(const double *const (&cp)[MAXK], lon
 #define ABN_LEAN_TMA 0
 #endif
 
+// Queue discipline of the streaming kernel. 0: every warp pulls its next fit on its own. 1: the CTA pulls FIT_WARPS
+// CONSECUTIVE fits at a time and its warps start them together: neighbours in cache order share the child and all
+// but the last parent, so the warps of a group read the same column tiles at about the same time and all but the
+// first find them in L1 (a warp that runs ahead misses and is caught up by the ones that hit). The price is the
+// barrier at the end of a group: warps whose fit needed fewer passes wait for the slowest of the eight.
+#ifndef ABN_GROUP_FETCH
+#define ABN_GROUP_FETCH 0
+#endif
+
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
@@ -1072,11 +1081,23 @@ fit_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs,
 #endif
     const double *lean_tab = exp256_tab + (ABN_EXP_REPLICATED ? (lane & (ABN_EXP64R_COPIES - 1)) : 0);
 
+#if ABN_GROUP_FETCH
+    __shared__ int group_base;
+#endif
     for (;;) {
+#if ABN_GROUP_FETCH
+        __syncthreads(); // the previous group is finished (and its base has been read by everybody)
+        if (threadIdx.x == 0) group_base = atomicAdd(counter, FIT_WARPS);
+        __syncthreads();
+        if (group_base >= count) break;
+        const int idx = group_base + warp;
+        if (idx >= count) continue;
+#else
         int idx = 0;
         if (lane == 0) idx = atomicAdd(counter, 1);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= count) break;
+#endif
         const int row = list[idx];
         const FitDesc d = descs[row];
         const int ch = child[row];
