@@ -26,6 +26,8 @@
 
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "fit_kernel.cuh"
 
 namespace ABN_NS {
@@ -253,6 +255,17 @@ __device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPla
 __host__ __device__ constexpr int cell_popc(int x) { return x == 0 ? 0 : (x & 1) + cell_popc(x >> 1); }
 __host__ __device__ constexpr int cell_ctz(int x) { return (x & 1) ? 0 : 1 + cell_ctz(x >> 1); }
 
+// f(integral_constant<I>) for I = I0 .. N-1: the subset loops below index register arrays, so every index has to be
+// a constant expression (a "#pragma unroll" over 63 subsets x 4 words is not honoured and the arrays go to local memory)
+template <int I, int N, typename F>
+__device__ __forceinline__ void cell_static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        cell_static_for<I + 1, N>(f);
+    }
+}
+
 template <int NP>
 __device__ __forceinline__ void cell_count_planes(const DataMeta &m, const CellPlan &cp, unsigned *tab)
 {
@@ -271,26 +284,28 @@ __device__ __forceinline__ void cell_count_planes(const DataMeta &m, const CellP
         for (int j = 0; j < NP; j++) v[j] = __ldg(pp[j] + q);
 #pragma unroll
         for (int w = 0; w < 4; w++) {
-            unsigned msk[NS];
-            msk[0] = 0xffffffffu;
+            unsigned pl[NP], msk[NS];
 #pragma unroll
-            for (int S = 1; S < NS; S++) {
-                const int j = cell_ctz(S), rest = S & (S - 1);
-                const unsigned pj = w == 0 ? v[j].x : (w == 1 ? v[j].y : (w == 2 ? v[j].z : v[j].w));
-                msk[S] = rest ? (msk[rest] & pj) : pj;
-                if (cell_popc(S) >= 3) cnt[S] += __popc(msk[S]);
-            }
+            for (int j = 0; j < NP; j++) pl[j] = w == 0 ? v[j].x : (w == 1 ? v[j].y : (w == 2 ? v[j].z : v[j].w));
+            // subsets in increasing order: the mask of S is the mask of (S without its lowest plane) AND that plane
+            cell_static_for<1, NS>([&](auto Sc) {
+                constexpr int S = decltype(Sc)::value;
+                constexpr int j = cell_ctz(S), rest = S & (S - 1);
+                if constexpr (rest == 0) msk[S] = pl[j];
+                else msk[S] = msk[rest] & pl[j];
+                if constexpr (cell_popc(S) >= 3) cnt[S] += __popc(msk[S]);
+            });
         }
     }
-#pragma unroll
-    for (int S = 1; S < NS; S++) {
-        if (cell_popc(S) >= 3) {
+    cell_static_for<1, NS>([&](auto Sc) {
+        constexpr int S = decltype(Sc)::value;
+        if constexpr (cell_popc(S) >= 3) {
             unsigned c = cnt[S];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
             if (lane == 0) tab[S] = c;
         }
-    }
+    });
     for (int S = lane; S < NS; S += 32) {
         const int pc = __popc(S);
         if (pc == 0) tab[S] = (unsigned)m.n;

@@ -14,10 +14,58 @@ namespace ABN_NS {
 constexpr int MN_UNROLL = 2;
 constexpr int MN_WARPS = 8; // warps per CTA (its per-warp BFGS state is 5.8 KB of static shared memory)
 
+// per warp: the tiles of the careful pass (design + indicator columns, 64 rows, FIT_STAGES) or of the lean pass
+// (design columns only, 128 rows, LEAN_STAGES), whichever is larger
+template <int L, int K, bool ICPT>
+constexpr size_t mn_stage_doubles_per_warp()
+{
+    const size_t careful = (size_t)FIT_STAGES * (K - (ICPT ? 1 : 0) + L - 1) * 32 * MN_UNROLL;
+    const size_t lean = (size_t)LEAN_STAGES * (K - (ICPT ? 1 : 0)) * LEAN_TROWS;
+    return careful > lean ? careful : lean;
+}
+// dynamic shared memory of a CTA: the tiles, then the pre-scaled exp table of the lean pass, then per warp
+// (design column)'(level indicator) of the fit in flight (the static 48 KB are taken by the BFGS states)
 template <int L, int K, bool ICPT>
 constexpr size_t mn_stage_bytes()
 {
-    return (size_t)MN_WARPS * FIT_STAGES * (K - (ICPT ? 1 : 0) + L - 1) * 32 * MN_UNROLL * sizeof(double);
+    return ((size_t)MN_WARPS * mn_stage_doubles_per_warp<L, K, ICPT>() + ABN_EXP256_N + (size_t)MN_WARPS * (L - 1) * K) * sizeof(double);
+}
+
+// The lean pass (rowops_mn.cuh mn_row_lean): the tiles, copies and row order of fit_kernel.cuh's lean passes, design
+// columns only. false: some linear predictor left (-700, 700) or is NaN - nothing written, the careful pass redoes it.
+template <int L, int K, bool ICPT>
+__device__ __forceinline__ bool mn_lean_pass(const double *const (&cp)[MAXK], const double *w_sm, const double *xty, long long n,
+                                             const double *tab256, const double *logtab, MnAcc *acc_sm, double *tile)
+{
+    constexpr int KD = K - (ICPT ? 1 : 0);
+    constexpr int KDA = KD > 0 ? KD : 1;
+    constexpr int NP = (L - 1) * K;
+    const int lane = threadIdx.x & 31;
+    double W[NP], g[NP], f = 0.0;
+#pragma unroll
+    for (int i = 0; i < NP; i++) { W[i] = w_sm[i]; g[i] = 0.0; }
+    RowTrack tk = row_track_init();
+    auto row = [&](const double (&x)[KDA]) -> int {
+        double o[L - 1];
+        mn_row_lean<L, K, ICPT>(x, W, tab256, logtab, f, g, o);
+#pragma unroll
+        for (int l = 1; l < L - 1; l++) {
+            const int h = hi_word(o[l]);
+            tk.smax = max(tk.smax, h);
+            tk.umax = max(tk.umax, (unsigned)h);
+        }
+        return hi_word(o[0]);
+    };
+    lean_stream<KD>(cp, n, tile, tk, row);
+    if (__any_sync(0xffffffffu, (tk.smax >= 0x4085E000) | (tk.umax >= 0xC085E000u))) return false;
+    f = warp_sum(f);
+#pragma unroll
+    for (int i = 0; i < NP; i++) g[i] = warp_sum(g[i]);
+    if (lane == 0) {
+        mn_lean_finish(NP, f, g, W, xty, &acc_sm->f, acc_sm->g);
+        acc_sm->bad = 0;
+    }
+    return true;
 }
 
 // same cp.async staging as warp_pass_staged (fit_kernel.cuh): each lane copies and reads back only
@@ -98,14 +146,19 @@ fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ des
     __shared__ MnAcc acc_all[MN_WARPS];
     __shared__ double exp_tab[ABN_EXP2_N];
     __shared__ double log_tab[128];
+    extern __shared__ __align__(16) double stage_tiles[];
+    double *const exp256_tab = stage_tiles + (size_t)MN_WARPS * mn_stage_doubles_per_warp<L, K, ICPT>();
+    double *const xty_all = exp256_tab + ABN_EXP256_N;
     if (threadIdx.x < ABN_EXP2_N) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
     if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
+    for (int j = threadIdx.x; j < ABN_EXP256_N; j += MN_WARPS * 32) exp256_tab[j] = exp256_entry(c_exp2_256_table[j], j);
     __syncthreads();
-    extern __shared__ __align__(16) double stage_tiles[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     MnState &st = st_all[warp];
     MnAcc *acc = &acc_all[warp];
-    double *tile = stage_tiles + (size_t)warp * FIT_STAGES * (K - (ICPT ? 1 : 0) + L - 1) * 32 * MN_UNROLL;
+    double *tile = stage_tiles + (size_t)warp * mn_stage_doubles_per_warp<L, K, ICPT>();
+    double *xty = xty_all + (size_t)warp * (L - 1) * K;
+    const bool lean_ok = !(c.flags & 1); // ABN_FLAG_EXACT_PATH: the row arithmetic of round 1 (response streamed, shifted softmax)
     for (;;) {
         int idx = 0;
         if (lane == 0) idx = atomicAdd(counter, 1);
@@ -125,11 +178,15 @@ fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ des
         if (lane == 0) {
             st.k = K; st.L = L; st.n = (double)m.n; st.rank = d.rank;
             more = mn_begin(st) ? 1 : 0;
+            for (int l = 1; l < L; l++)
+                for (int j = 0; j < K; j++) xty[(l - 1) * K + j] = m.G[(long long)gidx(d, j) * m.D + gram_col(d.ycol + l)];
         }
         more = __shfl_sync(0xffffffffu, more, 0);
         __syncwarp();
+        bool careful = !lean_ok;
         while (more) {
-            mn_warp_pass<L, K, ICPT>(y0, m.ld, cp, st.b, m.n, exp_tab, log_tab, acc, tile);
+            if (!careful && !mn_lean_pass<L, K, ICPT>(cp, st.b, xty, m.n, exp256_tab, log_tab, acc, tile)) careful = true;
+            if (careful) mn_warp_pass<L, K, ICPT>(y0, m.ld, cp, st.b, m.n, exp_tab, log_tab, acc, tile);
             __syncwarp();
             if (lane == 0) more = mn_consume(st, *acc) ? 1 : 0;
             more = __shfl_sync(0xffffffffu, more, 0);

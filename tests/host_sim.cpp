@@ -80,14 +80,45 @@ void run_pass(const DataMeta &m, const FitDesc &d, const Control &c, const FitSt
     else host_pass<RK_BIN_BAYES>(m, d, s.x, mode, a);
 }
 
-// multinomial child: value + gradient pass, dispatched to the same mn_row<L, K, ICPT> the kernel uses
+// multinomial child: value + gradient pass, dispatched to the same mn_row_lean / mn_row<L, K, ICPT> the kernel uses
+// (fit_mn_kernel.cuh: the lean pass first; the careful one for the rest of the fit once a linear predictor has left
+// (-700, 700), and always under ABN_FLAG_EXACT_PATH)
+static const double *host_exp256_table()
+{
+    static double tab[ABN_EXP256_N];
+    static bool done = false;
+    if (!done) { for (int j = 0; j < ABN_EXP256_N; j++) tab[j] = exp256_entry(h_exp2_256_table[j], j); done = true; }
+    return tab;
+}
+
 template <int L, int K, bool ICPT>
-void mn_host_pass(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a)
+void mn_host_pass(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a, bool &careful)
 {
     constexpr int NP = (L - 1) * K;
+    constexpr int KD = K - (ICPT ? 1 : 0);
     double W[NP], g[NP], f = 0.0;
     for (int i = 0; i < NP; i++) { W[i] = w[i]; g[i] = 0.0; }
     const double *y0 = m.X + (size_t)d.ycol * m.ld;
+    if (!careful) {
+        bool in_range = true;
+        for (long long i = 0; i < m.n && in_range; i++) {
+            double xd[KD > 0 ? KD : 1], o[L - 1];
+            for (int j = 0; j < KD; j++) xd[j] = m.X[(size_t)d.cols[j + (ICPT ? 1 : 0)] * m.ld + i];
+            mn_row_lean<L, K, ICPT>(xd, W, host_exp256_table(), host_log_table(), f, g, o);
+            for (int l = 0; l < L - 1; l++) in_range &= std::fabs(o[l]) < 700.0; // false for NaN
+        }
+        if (in_range) {
+            double xty[NP];
+            for (int l = 1; l < L; l++)
+                for (int j = 0; j < K; j++) xty[(l - 1) * K + j] = m.G[(size_t)gidx(d, j) * m.D + gram_col(d.ycol + l)];
+            mn_lean_finish(NP, f, g, W, xty, &a.f, a.g);
+            a.bad = 0;
+            return;
+        }
+        careful = true;
+        f = 0.0;
+        for (int i = 0; i < NP; i++) g[i] = 0.0;
+    }
     for (long long i = 0; i < m.n; i++) {
         double x[K], yl[L - 1];
         for (int j = 0; j < K; j++) x[j] = d.cols[j] < 0 ? 1.0 : m.X[(size_t)d.cols[j] * m.ld + i];
@@ -100,33 +131,33 @@ void mn_host_pass(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a
 }
 
 template <int L, int K>
-void mn_pass_k(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a)
+void mn_pass_k(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a, bool &careful)
 {
-    if (d.cols[0] < 0) mn_host_pass<L, K, true>(m, d, w, a); else mn_host_pass<L, K, false>(m, d, w, a);
+    if (d.cols[0] < 0) mn_host_pass<L, K, true>(m, d, w, a, careful); else mn_host_pass<L, K, false>(m, d, w, a, careful);
 }
 
 template <int L>
-void mn_pass_l(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a)
+void mn_pass_l(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a, bool &careful)
 {
     switch (d.k) {
-    case 1: mn_pass_k<L, 1>(m, d, w, a); break;
-    case 2: mn_pass_k<L, 2>(m, d, w, a); break;
-    case 3: mn_pass_k<L, 3>(m, d, w, a); break;
-    case 4: mn_pass_k<L, 4>(m, d, w, a); break;
-    case 5: mn_pass_k<L, 5>(m, d, w, a); break;
-    case 6: mn_pass_k<L, 6>(m, d, w, a); break;
-    case 7: mn_pass_k<L, 7>(m, d, w, a); break;
-    case 8: mn_pass_k<L, 8>(m, d, w, a); break;
+    case 1: mn_pass_k<L, 1>(m, d, w, a, careful); break;
+    case 2: mn_pass_k<L, 2>(m, d, w, a, careful); break;
+    case 3: mn_pass_k<L, 3>(m, d, w, a, careful); break;
+    case 4: mn_pass_k<L, 4>(m, d, w, a, careful); break;
+    case 5: mn_pass_k<L, 5>(m, d, w, a, careful); break;
+    case 6: mn_pass_k<L, 6>(m, d, w, a, careful); break;
+    case 7: mn_pass_k<L, 7>(m, d, w, a, careful); break;
+    case 8: mn_pass_k<L, 8>(m, d, w, a, careful); break;
     }
 }
 
-void mn_pass(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a)
+void mn_pass(const DataMeta &m, const FitDesc &d, const double *w, MnAcc &a, bool &careful)
 {
     switch (d.nlev) {
-    case 2: mn_pass_l<2>(m, d, w, a); break;
-    case 3: mn_pass_l<3>(m, d, w, a); break;
-    case 4: mn_pass_l<4>(m, d, w, a); break;
-    case 5: mn_pass_l<5>(m, d, w, a); break;
+    case 2: mn_pass_l<2>(m, d, w, a, careful); break;
+    case 3: mn_pass_l<3>(m, d, w, a, careful); break;
+    case 4: mn_pass_l<4>(m, d, w, a, careful); break;
+    case 5: mn_pass_l<5>(m, d, w, a, careful); break;
     }
 }
 
@@ -207,7 +238,8 @@ extern "C" int sim_score_cache(const abn_dataset *ds, const abn_candidates *cand
             s.k = d.k; s.L = d.nlev; s.n = (double)m.n; s.rank = d.rank;
             MnAcc a;
             bool more = mn_begin(s);
-            while (more) { mn_pass(m, d, s.b, a); more = mn_consume(s, a); }
+            bool careful = (ctrl->flags & ABN_FLAG_EXACT_PATH) != 0;
+            while (more) { mn_pass(m, d, s.b, a, careful); more = mn_consume(s, a); }
             ll = s.loglik; aic = s.aic; bic = s.bic; status = s.status; passes = s.passes;
         } else if (c.method == MLE && d.family == GAUSSIAN) {
             double x[MAXM], se[MAXM];
