@@ -125,12 +125,22 @@ __device__ __forceinline__ void cell_count_rows(const DataMeta &m, const CellPla
     // 16 rows per lane and step: one 16-byte load per column; the codes of 4 rows are combined at once when
     // the whole index fits a byte (<= 256 cells), otherwise row by row
     const bool bytewise = cp.total_bits <= 8 && !any_cap;
+    // the loads of step st + 1 are issued before the counters of step st are updated: the ~600 cycles of an L2 hit
+    // overlap the dependent shared-memory updates instead of preceding them
+    uint4 vn[NC];
+#pragma unroll
+    for (int j = 0; j < NC; j++) vn[j] = (lane < n16) ? __ldg(reinterpret_cast<const uint4 *>(colp[j]) + lane) : make_uint4(0u, 0u, 0u, 0u);
     for (long long st = 0; st < steps; st++) {
         const long long c = st * 32 + lane;
         const bool live = c < n16;
         uint4 v[NC];
 #pragma unroll
-        for (int j = 0; j < NC; j++) v[j] = live ? __ldg(reinterpret_cast<const uint4 *>(colp[j]) + c) : make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0; j < NC; j++) v[j] = vn[j];
+        {
+            const long long cn = c + 32;
+#pragma unroll
+            for (int j = 0; j < NC; j++) vn[j] = (cn < n16) ? __ldg(reinterpret_cast<const uint4 *>(colp[j]) + cn) : make_uint4(0u, 0u, 0u, 0u);
+        }
         unsigned cells[16];
         if (bytewise) {
             unsigned w[4] = {0u, 0u, 0u, 0u};
@@ -278,10 +288,15 @@ __device__ __forceinline__ void cell_count_planes(const DataMeta &m, const CellP
 #pragma unroll
     for (int S = 0; S < NS; S++) cnt[S] = 0u;
     const long long nq = m.ldb / 4; // 128 rows per 16-byte load; words beyond n are zero
+    uint4 vn[NP]; // loads of the next step in flight while this one is counted
+#pragma unroll
+    for (int j = 0; j < NP; j++) vn[j] = (lane < nq) ? __ldg(pp[j] + lane) : make_uint4(0u, 0u, 0u, 0u);
     for (long long q = lane; q < nq; q += 32) {
         uint4 v[NP];
 #pragma unroll
-        for (int j = 0; j < NP; j++) v[j] = __ldg(pp[j] + q);
+        for (int j = 0; j < NP; j++) v[j] = vn[j];
+#pragma unroll
+        for (int j = 0; j < NP; j++) vn[j] = (q + 32 < nq) ? __ldg(pp[j] + q + 32) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             unsigned pl[NP], msk[NS];
