@@ -62,7 +62,13 @@ __device__ __forceinline__ bool mn_lean_pass(const double *const (&cp)[MAXK], co
 #pragma unroll
     for (int i = 0; i < NP; i++) g[i] = warp_sum(g[i]);
     if (lane == 0) {
-        mn_lean_finish(NP, f, g, W, xty, &acc_sm->f, acc_sm->g);
+        if (xty) {
+            mn_lean_finish(NP, f, g, W, xty, &acc_sm->f, acc_sm->g);
+        } else { // partial sums of a row range (fit_mn_cta_kernel): the Gram terms are added once, after the ranges are summed
+            acc_sm->f = f;
+#pragma unroll
+            for (int i = 0; i < NP; i++) acc_sm->g[i] = g[i];
+        }
         acc_sm->bad = 0;
     }
     return true;
@@ -204,6 +210,109 @@ fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ des
     }
 }
 
+// ---- one fit per CTA ------------------------------------------------------------------------------------------
+// A multinomial fit is hundreds of passes (vmmin runs to its iteration cap on most of BASELINE's config 5: ~900
+// function evaluations of 500 000 rows), so with one warp per fit a GPU works on 2 368 fits of very different
+// lengths at a time and idles through the tail of every bucket - and a node's 92 171 parent sets are only ~5 waves
+// on 8 GPUs. Here the 8 warps of a CTA share ONE fit: warp w streams the w-th eighth of the row tiles, the per-warp
+// sums are added in warp order (fixed: results do not depend on scheduling), thread 0 runs vmmin and the next
+// weights are broadcast through shared memory. Fits are 8x shorter, the queue 8x finer.
+template <int L, int K, bool ICPT>
+__global__ void __launch_bounds__(MN_WARPS * 32, (L - 1) * K <= 16 ? 2 : 1)
+fit_mn_cta_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ list,
+                  int count, int *counter, ResultPtrs out)
+{
+    constexpr int NP = (L - 1) * K;
+    constexpr int KD = K - (ICPT ? 1 : 0);
+    __shared__ MnState st;
+    __shared__ MnAcc part[MN_WARPS];
+    __shared__ MnAcc acc;
+    __shared__ double xty[NP];
+    __shared__ double exp_tab[ABN_EXP2_N];
+    __shared__ double log_tab[128];
+    __shared__ double exp256_tab[ABN_EXP256_N];
+    __shared__ int sh_idx, sh_more, sh_careful, sh_lean_failed[MN_WARPS];
+    extern __shared__ __align__(16) double stage_tiles[];
+    if (threadIdx.x < ABN_EXP2_N) exp_tab[threadIdx.x] = c_exp2_table[threadIdx.x];
+    if (threadIdx.x < 64) fill_log_table(log_tab, threadIdx.x);
+    for (int j = threadIdx.x; j < ABN_EXP256_N; j += MN_WARPS * 32) exp256_tab[j] = exp256_entry(c_exp2_256_table[j], j);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *tile = stage_tiles + (size_t)warp * mn_stage_doubles_per_warp<L, K, ICPT>();
+    // rows of this warp: whole 128-row tiles, the last warp also takes what is left over
+    const long long ntiles = m.n / LEAN_TROWS;
+    const long long r0 = (ntiles * warp / MN_WARPS) * LEAN_TROWS;
+    const long long r1 = (warp == MN_WARPS - 1) ? m.n : (ntiles * (warp + 1) / MN_WARPS) * LEAN_TROWS;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh_idx = atomicAdd(counter, 1);
+        __syncthreads();
+        const int idx = sh_idx;
+        if (idx >= count) break;
+        const int row = list[idx];
+        const FitDesc d = descs[row];
+        const double *cp[MAXK];
+#pragma unroll
+        for (int j = 0; j < KD; j++) {
+            const int col = d.cols[j + (ICPT ? 1 : 0)];
+            cp[j] = m.X + (long long)(col < 0 ? 0 : col) * m.ld + r0;
+        }
+        const double *y0 = m.X + (long long)d.ycol * m.ld + r0;
+        if (threadIdx.x == 0) {
+            st.k = K; st.L = L; st.n = (double)m.n; st.rank = d.rank;
+            sh_more = mn_begin(st) ? 1 : 0;
+            sh_careful = (c.flags & 1) ? 1 : 0;
+            for (int l = 1; l < L; l++)
+                for (int j = 0; j < K; j++) xty[(l - 1) * K + j] = m.G[(long long)gidx(d, j) * m.D + gram_col(d.ycol + l)];
+        }
+        __syncthreads();
+        while (sh_more) {
+            bool careful = sh_careful != 0;
+            if (!careful) {
+                const bool ok = mn_lean_pass<L, K, ICPT>(cp, st.b, nullptr, r1 - r0, exp256_tab, log_tab, &part[warp], tile);
+                if (lane == 0) sh_lean_failed[warp] = ok ? 0 : 1;
+                __syncthreads();
+                bool any = false;
+#pragma unroll
+                for (int w = 0; w < MN_WARPS; w++) any |= sh_lean_failed[w] != 0;
+                careful = any; // some range left (-700, 700): every warp redoes its range with the careful pass
+            }
+            if (careful) {
+                mn_warp_pass<L, K, ICPT>(y0, m.ld, cp, st.b, r1 - r0, exp_tab, log_tab, &part[warp], tile);
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                double f = 0.0, g[NP];
+                for (int i = 0; i < NP; i++) g[i] = 0.0;
+                for (int w = 0; w < MN_WARPS; w++) { // warp order: fixed
+                    f += part[w].f;
+                    for (int i = 0; i < NP; i++) g[i] += part[w].g[i];
+                }
+                if (careful) {
+                    acc.f = f;
+                    for (int i = 0; i < NP; i++) acc.g[i] = g[i];
+                } else {
+                    mn_lean_finish(NP, f, g, st.b, xty, &acc.f, acc.g);
+                }
+                acc.bad = 0;
+                sh_careful = careful ? 1 : 0;
+                sh_more = mn_consume(st, acc) ? 1 : 0;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            if (out.mlik) out.mlik[row] = st.loglik;
+            if (out.aic) out.aic[row] = st.aic;
+            if (out.bic) out.bic[row] = st.bic;
+            if (out.mdl) out.mdl[row] = mdl_of(st.bic, d, c.nvars);
+            if (out.status) out.status[row] = st.status;
+            if (out.iters) out.iters[row] = st.passes;
+        }
+    }
+}
+
+// rows from which a fit is spread over a CTA: every warp gets at least 8 tiles
+constexpr long long MN_CTA_MIN_ROWS = (long long)MN_WARPS * 8 * LEAN_TROWS;
+
 typedef cudaError_t (*MnLaunchFn)(const DataMeta &, const Control &, const FitDesc *, const int *, int, int *, ResultPtrs,
                                   int grid, cudaStream_t);
 
@@ -216,6 +325,20 @@ cudaError_t launch_mn(const DataMeta &m, const Control &c, const FitDesc *descs,
     if (first_launch_on_device(configured)) {
         cudaError_t e = cudaFuncSetAttribute(fit_mn_kernel<L, K, ICPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+    }
+    if (m.n >= MN_CTA_MIN_ROWS) {
+        static bool configured_cta[64] = {false};
+        if (first_launch_on_device(configured_cta)) {
+            cudaError_t e = cudaFuncSetAttribute(fit_mn_cta_kernel<L, K, ICPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int per_sm = (L - 1) * K <= 16 ? 2 : 1;
+        const int grid_cta = count < sms * per_sm ? count : sms * per_sm;
+        fit_mn_cta_kernel<L, K, ICPT><<<grid_cta, MN_WARPS * 32, smem, stream>>>(m, c, descs, list, count, counter, out);
+        return cudaGetLastError();
     }
     fit_mn_kernel<L, K, ICPT><<<grid, MN_WARPS * 32, smem, stream>>>(m, c, descs, list, count, counter, out);
     return cudaGetLastError();

@@ -440,10 +440,14 @@ def test_build_score_cache_api_runs_on_gpu():
         assert abs(m - g) / abs(g) < 1e-9
 
 
-def test_multinomial_child_and_parent_config5_small():
+@pytest.mark.parametrize("n", [6000, 20_077])
+def test_multinomial_child_and_parent_config5_small(n):
     """Shrunk BASELINE.json configs[4]: a 4-level multinomial node as child (nnet / BFGS path,
-    R/build_score_cache_mle.R:319-331) and as parent (one-hot columns, no intercept, :266-270)."""
-    names, data, dists, mp, _ = synth.make_config(5, n=6000, n_nodes=40)
+    R/build_score_cache_mle.R:319-331) and as parent (one-hot columns, no intercept, :266-270).
+    6 000 rows: one warp per fit (fit_mn_kernel); 20 077 rows (ragged last tile): one fit per CTA
+    (fit_mn_cta_kernel, from 8 192 rows). Both with the lean pass and, under ABN_FLAG_EXACT_PATH, with the
+    streamed-response pass: same flags, same pass counts."""
+    names, data, dists, mp, _ = synth.make_config(5, n=n, n_nodes=40)
     keep = ["g1", "b1", "p1", "g2", "b2", "m1"]
     data = {k: data[k] for k in keep}
     dists = {k: dists[k] for k in keep}
@@ -459,6 +463,12 @@ def test_multinomial_child_and_parent_config5_small():
         # nnet's BFGS stops on reltol 1e-8 of the objective: parity unpinned beyond that
         assert H.rel_err(res[k][m_child], ref[k][m_child]).max() < 1e-7, k
         assert H.rel_err(res[k][~m_child], ref[k][~m_child]).max() < TOL, k
+    exact = H.gpu_score(P, ch0[m_child], par[m_child], H.control("mle", d, **{"exact.path": True}))
+    assert np.array_equal(exact["status"], res["status"][m_child])
+    assert H.rel_err(exact["mlik"], res["mlik"][m_child]).max() < 1e-9
+    converged = res["status"][m_child] == 0
+    # same optimiser path: the pass counts agree (rounding may move a line search by a trial on a rare fit)
+    assert np.mean(exact["iters"][converged] == res["iters"][m_child][converged]) > 0.9
 
 
 @pytest.mark.parametrize("method", ["mle", "bayes"])
