@@ -68,10 +68,32 @@ def slab_from_dict(local: dict, rows: int, world: int, block: int = 1024, device
     return slab.to(device) if device is not None else slab
 
 
-def gather_slab(slab, rows: int, world: int, block: int = 1024, group=None, to_host: bool = True):
+_staging = {}
+
+
+def _pinned_staging(rows: int, ring: int = 2):
+    """Page-locked host buffers for the gathered results, (4, rows) float64 + (2, rows) int32, kept per size in a
+    ring of `ring`: a device-to-host copy into fresh pageable memory costs 15-30 ms for 84 MB (page faults + staged
+    DMA), into a resident pinned buffer 2 ms. The arrays gather_slab returns are views of these buffers and stay
+    valid until `ring` further calls with the same `rows` have been made."""
+    import torch
+    e = _staging.get(rows)
+    if e is None:
+        if len(_staging) >= 4:
+            _staging.clear()
+        e = {"next": 0, "bufs": [(torch.empty((4, rows), dtype=torch.float64, pin_memory=True),
+                                  torch.empty((2, rows), dtype=torch.int32, pin_memory=True)) for _ in range(ring)]}
+        _staging[rows] = e
+    b = e["bufs"][e["next"]]
+    e["next"] = (e["next"] + 1) % len(e["bufs"])
+    return b
+
+
+def gather_slab(slab, rows: int, world: int, block: int = 1024, group=None, to_host: bool = True, pinned: bool = False):
     """ONE all_gather of the per-rank slabs + un-interleave on the slab's device.
 
-    Returns a dict of arrays in cache order (numpy if to_host, else torch tensors on the device)."""
+    Returns a dict of arrays in cache order (numpy if to_host, else torch tensors on the device). pinned = True
+    (CUDA slabs only): the host arrays are views of reused page-locked staging buffers, see _pinned_staging."""
     import torch
     import torch.distributed as dist
 
@@ -92,8 +114,15 @@ def gather_slab(slab, rows: int, world: int, block: int = 1024, group=None, to_h
         out = {k: dbl[f] for f, k in enumerate(FIELDS)}
         out["status"], out["iters"] = ints[0], ints[1]
         return out
-    dbl_h = dbl.contiguous().cpu().numpy()
-    ints_h = ints.contiguous().cpu().numpy()
+    if pinned and slab.is_cuda:
+        dbl_p, ints_p = _pinned_staging(rows)  # (an existing ring is reused whatever its length)
+        dbl_p.copy_(dbl, non_blocking=True)
+        ints_p.copy_(ints, non_blocking=True)
+        torch.cuda.current_stream(slab.device).synchronize()
+        dbl_h, ints_h = dbl_p.numpy(), ints_p.numpy()
+    else:
+        dbl_h = dbl.contiguous().cpu().numpy()
+        ints_h = ints.contiguous().cpu().numpy()
     out = {k: dbl_h[f] for f, k in enumerate(FIELDS)}
     out["status"], out["iters"] = ints_h[0], ints_h[1]
     return out

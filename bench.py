@@ -272,7 +272,7 @@ def main():
             for k in t["kernels"]:
                 e = acc["kernels"].setdefault(k["name"], {"ms": 0.0, "bytes": 0, "fits": 0, "launches": 0, "fp64": 0})
                 e["ms"] += k["ms"]; e["bytes"] += k["bytes"]; e["fits"] += k["fits"]; e["launches"] += 1; e["fp64"] += k["fp64"]
-        return shard.gather_slab(slab, len(rows), world, args.block)
+        return shard.gather_slab(slab, len(rows), world, args.block, pinned=True)
 
     for w in range(args.warmup):
         run_step(w, False)
