@@ -655,7 +655,7 @@ ABN_HDN int hy_after_iterate(FitState &s, const Control &c, int gsl_status)
 #ifndef ABN_SHORTCUT
 #define ABN_SHORTCUT 1
 #endif
-constexpr double SC_REL = 1e-11; // share of |loglik| each neglected term may reach // share of |loglik| each neglected term may reach // share of |loglik| each neglected term may reach // share of |loglik| each neglected term may reach
+constexpr double SC_REL = 1e-11; // share of |loglik| each neglected term may reach
 constexpr double SC_FULL_Q = 3e-4; // binomial: predicted eta-length under which the next pass also sums the loglik
 
 // bound on the cubic remainder of the Taylor step: the third derivative of either family's loglik
