@@ -11,6 +11,12 @@
 
 namespace ABN_NS {
 
+// CTAs per SM the multinomial kernels are compiled for when the fit has at most MN_SMALL_NP weights (2: 128 registers
+// per thread, 16 warps per SM; 1: 255 registers, 8 warps - room to interleave the four rows of a tile step)
+#ifndef ABN_MN_BLOCKS
+#define ABN_MN_BLOCKS 2
+#endif
+constexpr int MN_SMALL_NP = 16;
 constexpr int MN_UNROLL = 2;
 constexpr int MN_WARPS = 8; // warps per CTA (its per-warp BFGS state is 5.8 KB of static shared memory)
 
@@ -144,7 +150,7 @@ __device__ __forceinline__ void mn_warp_pass(const double *__restrict__ y0, long
 }
 
 template <int L, int K, bool ICPT>
-__global__ void __launch_bounds__(MN_WARPS * 32, (L - 1) * K <= 16 ? 2 : 1)
+__global__ void __launch_bounds__(MN_WARPS * 32, (L - 1) * K <= MN_SMALL_NP ? ABN_MN_BLOCKS : 1)
 fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ list,
               int count, int *counter, ResultPtrs out)
 {
@@ -218,7 +224,7 @@ fit_mn_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ des
 // sums are added in warp order (fixed: results do not depend on scheduling), thread 0 runs vmmin and the next
 // weights are broadcast through shared memory. Fits are 8x shorter, the queue 8x finer.
 template <int L, int K, bool ICPT>
-__global__ void __launch_bounds__(MN_WARPS * 32, (L - 1) * K <= 16 ? 2 : 1)
+__global__ void __launch_bounds__(MN_WARPS * 32, (L - 1) * K <= MN_SMALL_NP ? ABN_MN_BLOCKS : 1)
 fit_mn_cta_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ list,
                   int count, int *counter, ResultPtrs out)
 {
@@ -335,7 +341,7 @@ cudaError_t launch_mn(const DataMeta &m, const Control &c, const FitDesc *descs,
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int per_sm = (L - 1) * K <= 16 ? 2 : 1;
+        const int per_sm = (L - 1) * K <= MN_SMALL_NP ? ABN_MN_BLOCKS : 1;
         const int grid_cta = count < sms * per_sm ? count : sms * per_sm;
         fit_mn_cta_kernel<L, K, ICPT><<<grid_cta, MN_WARPS * 32, smem, stream>>>(m, c, descs, list, count, counter, out);
         return cudaGetLastError();
