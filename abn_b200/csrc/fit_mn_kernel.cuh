@@ -12,9 +12,10 @@
 namespace ABN_NS {
 
 // CTAs per SM the multinomial kernels are compiled for when the fit has at most MN_SMALL_NP weights (2: 128 registers
-// per thread, 16 warps per SM; 1: 255 registers, 8 warps - room to interleave the four rows of a tile step)
+// per thread, 16 warps per SM; 1: 255 registers, 8 warps - room to interleave the four rows of a tile step).
+// Measured on the config-5 slice of tests/run_mn_slice.py (one box): 12.17 s with 2, 11.26 s with 1.
 #ifndef ABN_MN_BLOCKS
-#define ABN_MN_BLOCKS 2
+#define ABN_MN_BLOCKS 1
 #endif
 constexpr int MN_SMALL_NP = 16;
 constexpr int MN_UNROLL = 2;
