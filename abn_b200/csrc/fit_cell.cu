@@ -15,11 +15,11 @@ static cudaError_t launch_cell(const DataMeta &m, const Control &c, const FitDes
         cudaError_t e = cudaFuncSetAttribute(fit_cell_kernel<KIND, CAPBITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const int per_sm = CAPBITS == CELL_SMALL_CAPBITS ? 4 : 2;
+    const int per_sm = CAPBITS == CELL_SMALL_CAPBITS ? 4 : CELL_LARGE_PER_SM;
     const int grid = std::min((count + CELL_WARPS - 1) / CELL_WARPS, sm_count * per_sm);
     // overflow-list slots (DataMeta::cell_ovf): [binomial small | binomial large | Poisson small | Poisson large], each
     // sized for its largest grid, so that the four kernels can run side by side
-    const int small_slots = sm_count * 4 * CELL_WARPS, large_slots = sm_count * 2 * CELL_WARPS;
+    const int small_slots = sm_count * 4 * CELL_WARPS, large_slots = sm_count * CELL_LARGE_PER_SM * CELL_WARPS;
     const int fam = (KIND == RK_POIS) ? 1 : 0;
     const int slot0 = fam * (small_slots + large_slots) + (CAPBITS == CELL_SMALL_CAPBITS ? 0 : small_slots);
     fit_cell_kernel<KIND, CAPBITS><<<grid, CELL_WARPS * 32, smem, stream>>>(m, c, descs, child, list, count, counter, out, slot0);
@@ -35,7 +35,7 @@ static cudaError_t launch_cell_kind(int kind, const DataMeta &m, const Control &
     return launch_cell<RK_BIN_MLE, CAPBITS>(m, c, descs, child, list, count, counter, out, sm_count, stream);
 }
 
-int abn_cell_ovf_slots(int sm_count) { return 2 * (sm_count * 4 * CELL_WARPS + sm_count * 2 * CELL_WARPS); }
+int abn_cell_ovf_slots(int sm_count) { return 2 * (sm_count * 4 * CELL_WARPS + sm_count * CELL_LARGE_PER_SM * CELL_WARPS); }
 
 cudaError_t abn_cell_launch(int kind, int large, const abnc::DataMeta &m, const abnc::Control &c, const abn::FitDesc *descs,
                             const int *child, const int *list, int count, int *counter, abnc::ResultPtrs out,

@@ -32,12 +32,18 @@
 
 namespace ABN_NS {
 
-// Two table sizes, two kernel instantiations: small tables leave room for twice the warps per SM (the whole
-// kernel is latency-bound: dependent shared-memory updates, a serial solver on lane 0)
+// Two table classes, two kernel instantiations, both at 16 warps per SM (the whole kernel is latency-bound: dependent
+// shared-memory updates, a serial solver on lane 0 - warps are what hides it)
 constexpr int CELL_SMALL_CAPBITS = 11;    // cell index <= 6 bits: 2 048 counters per warp (8 KB), 16 warps per SM
-constexpr int CELL_LARGE_CAPBITS = 12;    // cell index 7..10 bits: 4 096 counters per warp (16 KB), 8 warps per SM
+#ifndef ABN_CELL_LARGE_CAPBITS
+#define ABN_CELL_LARGE_CAPBITS 10
+#endif
+// cell index 7..10 bits. 12: 4 096 counters per warp (16 KB, 4..32 replicas per counter), 8 warps per SM.
+// 10: 1 024 counters (4 KB), at most 8 replicas - every update is a shared-memory atomic - and 16 warps per SM
+constexpr int CELL_LARGE_CAPBITS = ABN_CELL_LARGE_CAPBITS;
+constexpr int CELL_LARGE_PER_SM = CELL_LARGE_CAPBITS <= 10 ? 4 : 2; // CTAs per SM the large-table kernel is built for
 constexpr int CELL_SMALL_BITS = 6;
-constexpr int CELL_MAX_BITS = 10;         // widest cell index taken: at least 4 replicas per counter (<= 8 phases)
+constexpr int CELL_MAX_BITS = 10;         // widest cell index taken
 constexpr int CELL_WARPS = 4;             // warps per CTA
 #ifndef ABN_CELL_ATOMIC_PHASES
 #define ABN_CELL_ATOMIC_PHASES 4
@@ -513,7 +519,7 @@ __device__ __forceinline__ void cell_pass_any(const DataMeta &m, const CellPlan 
 }
 
 template <int KIND, int CAPBITS>
-__global__ void __launch_bounds__(CELL_WARPS * 32, CAPBITS == CELL_SMALL_CAPBITS ? 4 : 2)
+__global__ void __launch_bounds__(CELL_WARPS * 32, CAPBITS == CELL_SMALL_CAPBITS ? 4 : CELL_LARGE_PER_SM)
 fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ child,
                 const int *__restrict__ list, int count, int *counter, ResultPtrs out, int ovf_slot0)
 {
