@@ -249,7 +249,7 @@ def kernel_name(kid: int) -> str:
         return "gauss_kernel"
     cell0 = 2 + 6 * (capi.FAST_K + 1) * 2  # plan.cuh CELL_BUCKET0
     if kid >= cell0:
-        return f"fit_cell_kernel<{('binomial', 'poisson')[(kid - cell0) >> 1]},{('small', 'large')[(kid - cell0) & 1]}>"
+        return f"fit_cell_kernel<{('binomial', 'poisson')[(kid - cell0) // 3]},{('small', 'large', 'planes')[(kid - cell0) % 3]}>"
     code = kid - 2
     icpt, fk = code & 1, code >> 1
     fam, k = divmod(fk, capi.FAST_K + 1)

@@ -29,7 +29,7 @@ cudaError_t abn_wide_launch(const abnc::DataMeta &m, const abnc::Control &c, con
 int abn_wide_max_k();
 int abn_cell_ovf_slots(int sm_count); // fit_cell.cu: warps of all contingency-table kernels that may run together
 // fit_cell.cu: all-discrete designs on contingency tables (kind: RK_BIN_MLE, RK_POIS, RK_BIN_BAYES)
-cudaError_t abn_cell_launch(int kind, int large, const abnc::DataMeta &m, const abnc::Control &c, const abn::FitDesc *descs,
+cudaError_t abn_cell_launch(int kind, int cls, const abnc::DataMeta &m, const abnc::Control &c, const abn::FitDesc *descs,
                             const int *child, const int *list, int count, int *counter, abnc::ResultPtrs out,
                             int sm_count, cudaStream_t stream);
 
@@ -365,7 +365,7 @@ __global__ void resolve_kernel(const DataMeta m, int method, int flags, long lon
     descs[r] = d;
     int key = bucket_of(d);
     const int cell = cell_eligible(m, d, method, flags);
-    if (cell) key = CELL_BUCKET0 + (d.family == POISSON ? 2 : 0) + (cell - 1);
+    if (cell) key = CELL_BUCKET0 + (d.family == POISSON ? 3 : 0) + (cell - 1);
     keys[r] = (unsigned char)key;
     idx[r] = (int)r;
 }
@@ -959,8 +959,8 @@ static int score_impl(abn_data *d, const abn_candidates *cand, bool resident, co
             } else if (b == 1) {
                 gauss_kernel<<<(count + 127) / 128, 128, 0, ks>>>(d->m, c, d->dDescs, d->dChild, list, count, rp);
             } else if (b >= CELL_BUCKET0) {
-                const int kind = (b >= CELL_BUCKET0 + 2) ? RK_POIS : (c.method == MLE ? RK_BIN_MLE : RK_BIN_BAYES);
-                CUDA_TRY(abn_cell_launch(kind, (b - CELL_BUCKET0) & 1, d->m, c, d->dDescs, d->dChild, list, count, slot, rp, d->sm_count, ks));
+                const int kind = (b >= CELL_BUCKET0 + 3) ? RK_POIS : (c.method == MLE ? RK_BIN_MLE : RK_BIN_BAYES);
+                CUDA_TRY(abn_cell_launch(kind, (b - CELL_BUCKET0) % 3, d->m, c, d->dDescs, d->dChild, list, count, slot, rp, d->sm_count, ks));
             } else {
                 const int code = b - 2, icpt = code & 1, fk = code >> 1, fam = fk / (MAXK + 1), k = fk % (MAXK + 1);
                 FitLaunchFn fn = nullptr;

@@ -43,6 +43,11 @@ constexpr int CELL_SMALL_CAPBITS = 11;    // cell index <= 6 bits: 2 048 counter
 constexpr int CELL_LARGE_CAPBITS = ABN_CELL_LARGE_CAPBITS;
 constexpr int CELL_LARGE_PER_SM = CELL_LARGE_CAPBITS <= 10 ? 4 : 2; // CTAs per SM the large-table kernel is built for
 constexpr int CELL_SMALL_BITS = 6;
+// all-binary designs (every byte column has codes 0 / 1, bit planes built): the table comes out of registers
+// (cell_count_planes), shared memory holds just the 64 cells, and the kernel is built for 24 warps per SM - the
+// solver on lane 0 is latency-bound and warps are what hides it (-18 % on config 3 against 16 warps per SM)
+constexpr int CELL_PLANES_CAPBITS = 7;
+constexpr int CELL_PLANES_PER_SM = 6;
 constexpr int CELL_MAX_BITS = 10;         // widest cell index taken
 constexpr int CELL_WARPS = 4;             // warps per CTA
 #ifndef ABN_CELL_ATOMIC_PHASES
@@ -68,7 +73,7 @@ ABN_HD int cell_bits_of(const DataMeta &m, int col, bool *capped)
     return b;
 }
 
-// Is this resolved design one the cell kernel takes? 0 = no, 1 = small table, 2 = large table (called by
+// Is this resolved design one the cell kernel takes? 0 = no, 1 = small table, 2 = large table, 3 = bit planes (called by
 // resolve_kernel; host builds have no byte codes and never say yes)
 ABN_HD int cell_eligible(const DataMeta &m, const FitDesc &d, int method, int flags)
 {
@@ -77,15 +82,18 @@ ABN_HD int cell_eligible(const DataMeta &m, const FitDesc &d, int method, int fl
     if (d.family == POISSON && method == MLE && (flags & 1)) return 0; // the reference's start-value pass needs y per row
     int bits = (d.family == BINOMIAL) ? 1 : 0;                             // the response is part of a binomial cell
     int ncapped = 0;
+    bool binary = true; // every design column has codes 0 / 1 (the response of a binomial child always has)
     for (int j = 0; j < d.k; j++) {
         if (d.cols[j] < 0) continue;
         if (m.col_card[d.cols[j]] <= 0) return 0;
+        binary &= m.col_card[d.cols[j]] <= 2;
         bool capped;
         bits += cell_bits_of(m, d.cols[j], &capped);
         ncapped += capped;
     }
     if (d.family == BINOMIAL && m.col_card[d.ycol] != 2) return 0;
     if (ncapped > 4) return 0; // the overflow list holds n / 8 rows: 4 columns x n / 32
+    if (binary && m.Xb != nullptr && bits >= 1 && bits <= CELL_SMALL_BITS) return 3;
     return bits <= CELL_SMALL_BITS ? 1 : (bits <= CELL_MAX_BITS ? 2 : 0);
 }
 
@@ -519,7 +527,7 @@ __device__ __forceinline__ void cell_pass_any(const DataMeta &m, const CellPlan 
 }
 
 template <int KIND, int CAPBITS>
-__global__ void __launch_bounds__(CELL_WARPS * 32, CAPBITS == CELL_SMALL_CAPBITS ? 4 : CELL_LARGE_PER_SM)
+__global__ void __launch_bounds__(CELL_WARPS * 32, CAPBITS == CELL_PLANES_CAPBITS ? CELL_PLANES_PER_SM : (CAPBITS == CELL_SMALL_CAPBITS ? 4 : CELL_LARGE_PER_SM))
 fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ descs, const int *__restrict__ child,
                 const int *__restrict__ list, int count, int *counter, ResultPtrs out, int ovf_slot0)
 {
@@ -541,7 +549,8 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
     double *xty = xty_all[warp];
     unsigned *tab = cell_tabs + (size_t)warp * (CAP + 32);
     // this warp's overflow list (row indices beyond a cap); `ovf_slot0` separates the kernels that may run together
-    unsigned *ovf = m.cell_ovf ? m.cell_ovf + ((long long)ovf_slot0 + (long long)blockIdx.x * CELL_WARPS + warp) * m.cell_ovf_stride : nullptr;
+    unsigned *ovf = (m.cell_ovf && CAPBITS != CELL_PLANES_CAPBITS) // binary columns are never capped: the bit-plane kernel owns no list
+                        ? m.cell_ovf + ((long long)ovf_slot0 + (long long)blockIdx.x * CELL_WARPS + warp) * m.cell_ovf_stride : nullptr;
 
     for (;;) {
         int idx = 0;
@@ -581,7 +590,7 @@ fit_cell_kernel(const DataMeta m, const Control c, const FitDesc *__restrict__ d
         }
         __syncwarp();
         const int tb = cp.total_bits;
-        if (CAPBITS == CELL_SMALL_CAPBITS && cp.all_binary && cp.ncol >= 1) {
+        if ((CAPBITS == CELL_PLANES_CAPBITS || CAPBITS == CELL_SMALL_CAPBITS) && cp.all_binary && cp.ncol >= 1) {
             switch (cp.ncol) {
             case 1: cell_count_planes<1>(m, cp, tab); break;
             case 2: cell_count_planes<2>(m, cp, tab); break;

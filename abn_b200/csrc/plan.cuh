@@ -47,9 +47,9 @@ ABN_HD int bucket_of(const FitDesc &d)
 }
 constexpr int NBUCKETS = 2 + NFAMSLOT * (MAXK + 1) * 2;
 // all-discrete designs (fit_cell.cuh) get four buckets of their own after the streaming ones:
-// CELL_BUCKET0 + 2 * (Poisson child) + (large table)
+// CELL_BUCKET0 + 3 * (Poisson child) + class (0: small table, 1: large table, 2: all-binary design on bit planes)
 constexpr int CELL_BUCKET0 = NBUCKETS;
-constexpr int NBUCKETS_ALL = NBUCKETS + 4;
+constexpr int NBUCKETS_ALL = NBUCKETS + 6;
 static_assert(MAXK > 8 || NBUCKETS_ALL <= 256, "bucket keys are bytes (the wide build does not bucket)");
 
 ABN_HD int gidx(const FitDesc &d, int j) { return d.cols[j] < 0 ? 0 : 1 + d.cols[j]; }

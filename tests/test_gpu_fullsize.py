@@ -50,7 +50,7 @@ def test_config3_full_size():
     with abncache.DeviceData(P) as dev:
         res = dev.score(ch0, par, ctrl)
         kernels = {k["name"] for k in dev.timing()["kernels"]}
-    assert "fit_cell_kernel<binomial,small>" in kernels          # every design is all-discrete: contingency tables
+    assert kernels == {"fit_cell_kernel<binomial,planes>"}        # every design is all-binary: tables from bit planes
     assert (res["status"] == 0).all() and np.isfinite(res["mlik"]).all()
     k_par = (par >= 0).sum(axis=1)
     n = P.X.shape[0]
