@@ -84,3 +84,33 @@ def test_binomial_columns_are_validated_and_recoded_like_the_reference():
         prep.prepare({"b": rng.integers(0, 3, 40), "g": g}, {"b": "binomial", "g": "gaussian"}, "mle")
     with pytest.raises(ValueError, match="both cases"):
         prep.prepare({"b": np.zeros(40), "g": g}, {"b": "binomial", "g": "gaussian"}, "bayes")
+
+
+def test_kernel_names_cover_every_bucket_of_the_plan():
+    """abn_timing.kernel_id -> name (plan.cuh: wide, Gaussian, 2 x (families x K x intercept), then the table kernels
+    CELL_BUCKET0 + 3 * (Poisson child) + class)."""
+    from abn_b200 import _capi as capi
+    cell0 = 2 + 6 * (capi.FAST_K + 1) * 2
+    assert abncache.kernel_name(0) == "fit_wide_kernel" and abncache.kernel_name(1) == "gauss_kernel"
+    assert abncache.kernel_name(2 + 2 * 4 + 1) == "fit_kernel<binomial,K=4,icpt=1>"
+    assert abncache.kernel_name(2 + 2 * ((capi.FAST_K + 1) + 4) + 1) == "fit_kernel<poisson,K=4,icpt=1>"
+    names = [abncache.kernel_name(cell0 + i) for i in range(6)]
+    assert names == ["fit_cell_kernel<binomial,small>", "fit_cell_kernel<binomial,large>", "fit_cell_kernel<binomial,planes>",
+                     "fit_cell_kernel<poisson,small>", "fit_cell_kernel<poisson,large>", "fit_cell_kernel<poisson,planes>"]
+
+
+def test_gather_slab_on_the_host_ignores_the_pinned_switch():
+    """shard.gather_slab(pinned=True) stages through page-locked buffers for CUDA slabs only; a host slab (the gloo
+    tests, callers without a device) takes the plain path and returns the same arrays."""
+    import torch
+    from abn_b200 import shard
+    rows, block = 5000, 512
+    rng = np.random.default_rng(3)
+    local = {"mlik": rng.normal(size=rows), "aic": rng.normal(size=rows), "bic": rng.normal(size=rows), "mdl": rng.normal(size=rows),
+             "status": rng.integers(0, 3, rows).astype(np.int32), "iters": rng.integers(0, 99, rows).astype(np.int32)}
+    slab = shard.slab_from_dict(local, rows, 1, block)
+    assert isinstance(slab, torch.Tensor) and not slab.is_cuda
+    for pinned in (False, True):
+        out = shard.gather_slab(slab, rows, 1, block, pinned=pinned)
+        for k, v in local.items():
+            assert np.array_equal(out[k], v), (pinned, k)
